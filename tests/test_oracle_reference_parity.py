@@ -1,0 +1,234 @@
+"""Pins the oracle (restatement) against outputs of the REAL reference code and against the
+reference's own known-answer tests.  CPU only."""
+import itertools
+import math
+
+import numpy
+import pytest
+
+from conftest import close
+from oracle import cport, halton, objectives as ob, pipeline, saltelli, scale, sobol
+
+A6 = [0, 0.5, 3, 9, 99, 99]
+
+
+# ---- varsens/scale.py doctests and varsens/tests/test_scaling.py known answers -------------
+def test_scale_doctests():
+    a = numpy.array
+    numpy.testing.assert_allclose(scale.linear(a([0.5] * 3), a([-100, -10, 1000]), a([100, 20, 2000])),
+                                  [0.0, 5.0, 1500.0], rtol=0, atol=1e-12)                       # scale.py:28-29
+    # :57-58 -- the docstring's third value (1414.21356237) is what ub=2000 gives; with the printed
+    # ub=2500 the reference's own code returns 1000*sqrt(2.5) (checked by running it: refgold).
+    numpy.testing.assert_allclose(scale.power(a([0.5] * 3), a([10, 100, 1000]), a([1000, 200, 2500])),
+                                  [100.0, 141.42135624, 1000.0 * math.sqrt(2.5)], rtol=1e-10)
+    numpy.testing.assert_allclose(scale.percentage(a([0.333] * 3), a([1, 10, 1000]), 50.0),
+                                  [0.833, 8.33, 833.0], rtol=1e-12)                              # :85-86
+    numpy.testing.assert_allclose(scale.magnitude(a([0.333] * 3), a([1, 10, 1000])),
+                                  [0.09954054, 0.99540542, 99.54054174], rtol=1e-7)              # :116-117
+
+
+def test_scale_known_answers():
+    a, n = numpy.array, 5
+    p = a(range(n)) / (n - 1.0)
+    s10 = math.sqrt(0.1)
+    cases = [
+        (scale.linear(p, a([-100] * n), a([100] * n)), [-100.0, -50.0, 0.0, 50.0, 100.0]),             # test_scaling.py:5-11
+        (scale.linear(a([0] * 3), a([-100, -10, 1000]), a([100, 20, 2000])), [-100.0, -10.0, 1000.0]),  # :13-18
+        (scale.linear(a([1.0] * 3), a([-100, -10, 1000]), a([100, 20, 2000])), [100.0, 20.0, 2000.0]),  # :20-25
+        (scale.power(p, a([1] * n), a([100] * n)), [1.0, 10 * s10, 10.0, 100 * s10, 100.0]),           # :27-33
+        (scale.power(a([0] * 3), a([1, 10, 1000]), a([100, 20, 2000])), [1, 10, 1000]),                 # :35-40
+        (scale.power(a([1.0] * 3), a([1, 10, 1000]), a([100, 20, 2000])), [100.0, 20.0, 2000.0]),       # :42-47
+        (scale.percentage(p, a([-10, -1, 0, 1, 20]), 33.0), [-6.7, -0.835, 0.0, 1.165, 26.6]),          # :49-55
+        (scale.magnitude(p, a([1, 10, 100, 1000, 1e4])), [0.001, s10, 100, s10 * 1e5, 1e7]),            # :57-63
+    ]
+    for got, want in cases:
+        numpy.testing.assert_allclose(got, want, rtol=0, atol=5e-8)   # assert_almost_equal = 7 places
+
+
+def test_scale_matches_reference_code(refgold):
+    p = refgold["scale_p"]
+    assert (scale.linear(p, -3.5, 12.25) == refgold["scale_linear"]).all()
+    assert (scale.power(p, 0.01, 250.0) == refgold["scale_power"]).all()
+    assert (scale.percentage(p, 40.0, 33.0) == refgold["scale_percentage"]).all()
+    assert (scale.magnitude(p, 2.5, 2.0, 10.0) == refgold["scale_magnitude"]).all()
+
+
+# ---- Sample / Objective / Varsens against the real reference's outputs ------------------------
+def test_c1_sample_and_indices_match_reference_code(refgold):
+    s = saltelli.Sample(6, 1024, lambda x: x, verbose=False)
+    f = s.flat()
+    assert (f[:8] == refgold["c1_flat_head"]).all() and (f[-8:] == refgold["c1_flat_tail"]).all()
+    assert (f[refgold["c1_flat_rows_probe"]] == refgold["c1_flat_probe"]).all()
+    o = saltelli.Objective(6, 1024, s, lambda x: ob.g_function_row(x, A6), verbose=False)
+    assert (o.flat() == refgold["c1_obj_flat"]).all()
+    v = saltelli.Varsens(o, verbose=False)
+    for name in ("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t", "sens_2", "sens_2n"):
+        assert (numpy.asarray(getattr(v, name)) == refgold["c1_" + name]).all(), name
+
+
+def test_intended_varsens_route_equals_three_step_route(refgold):
+    v = saltelli.Varsens(lambda x: ob.g_function_row(x, A6), lambda x: x, 6, 1024, verbose=False)
+    for name in ("E_2", "var_y", "sens", "sens_t", "sens_2", "sens_2n"):
+        assert (numpy.asarray(getattr(v, name)) == refgold["c1_" + name]).all(), name
+
+
+def test_two_output_objective_matches_reference_code(refgold):
+    s = saltelli.Sample(6, 256, lambda x: x, verbose=False)
+    o = saltelli.Objective(6, 256, s, lambda x: [ob.g_function_row(x, A6), ob.g_function_row(x, A6[::-1])],
+                           verbose=False)
+    assert (o.flat() == refgold["two_obj_flat"]).all()
+    v = saltelli.Varsens(o, verbose=False)
+    for name in ("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t", "sens_2", "sens_2n"):
+        got = numpy.asarray(getattr(v, name))
+        assert got.shape == refgold["two_" + name].shape and (got == refgold["two_" + name]).all(), name
+    assert v.sens_2.shape == (6, 2, 6, 2)
+
+
+def test_scaled_samples_match_reference_code(refgold):
+    lb, ub = refgold["lin_lb"], refgold["lin_ub"]
+    s = saltelli.Sample(5, 13, lambda x: scale.linear(x, lb, ub), discard=7, verbose=False)
+    assert (s.flat() == refgold["lin_flat_k5_n13_discard7"]).all()
+    assert (cport.sample_flat(5, 13, discard=7, scale=("linear", lb, ub)) == refgold["lin_flat_k5_n13_discard7"]).all()
+    ref = refgold["mag_ref"]
+    s = saltelli.Sample(4, 9, lambda x: scale.magnitude(x, ref, orders=1.0), verbose=False)
+    assert (s.flat() == refgold["mag_flat_k4_n9"]).all()
+    s = saltelli.Sample(3, 11, lambda x: scale.percentage(x, numpy.array([1.0, 10.0, 1000.0]), 33.0), verbose=False)
+    assert (s.flat() == refgold["pct_flat_k3_n11"]).all()
+
+
+def test_raw_entry_matches_reference_code(refgold):
+    raw = refgold["raw_in"].copy()
+    s = saltelli.Sample(4, 10, lambda x: scale.linear(x, -1.0, 2.0), raw=raw, verbose=False)
+    assert (s.flat() == refgold["raw_flat_k4_n10"]).all()
+    got = cport.sample_flat(4, 10, scale=("linear", [-1.0] * 4, [2.0] * 4), raw=refgold["raw_in"])
+    assert (got == refgold["raw_flat_k4_n10"]).all()
+
+
+def test_nan_trimming_matches_reference_code(refgold, capsys):
+    o = saltelli.Objective(6, 256, objective_vals=refgold["nan_obj_in"], verbose=False)
+    assert tuple(o.fM_1.shape) == tuple(refgold["nan_fM_1_shape"])
+    v = saltelli.Varsens(o, verbose=False)
+    for name in ("E_2", "var_y", "sens", "sens_t", "sens_2"):
+        assert (numpy.asarray(getattr(v, name)) == refgold["nan_" + name]).all(), name
+    assert "WARNING: 2 of 3584 objectives were NaN" in capsys.readouterr().out
+
+
+# ---- reference unit tests restated (varsens/tests/test_sample.py, test_objective.py) ----------
+def test_sample_shapes_range_structure():
+    x = saltelli.Sample(11, 13, lambda x: x, verbose=False)                        # test_sample.py:5-21
+    assert x.M_1.shape == (13, 11) and x.M_2.shape == (13, 11)
+    assert x.N_j.shape == (11, 13, 11) and x.N_nj.shape == (11, 13, 11)
+    x = saltelli.Sample(7, 11, lambda x: x, verbose=False)                         # :23-42
+    for m in (x.M_1, x.M_2, x.N_j, x.N_nj):
+        assert (m >= 0).all() and (m <= 1).all()
+    x = saltelli.Sample(3, 5, lambda x: x, verbose=False)                          # :44-54
+    for i in range(3):
+        assert (x.M_1[:, i] == x.N_j[i][:, i]).all() and (x.M_2[:, i] == x.N_nj[i][:, i]).all()
+        for j in range(3):
+            if j != i:
+                assert (x.M_1[:, j] == x.N_nj[i][:, j]).all() and (x.M_2[:, j] == x.N_j[i][:, j]).all()
+    x = saltelli.Sample(17, 1024, lambda x: x, verbose=False)                      # :56-64
+    for m, d in ((x.M_1, 17), (x.M_2, 17), (x.N_j, 17 * 17), (x.N_nj, 17 * 17)):
+        assert abs(m.sum() / 1024 / d - 0.5) < 5e-3
+    s = saltelli.Sample(5, 13, lambda x: x, verbose=False)                         # :66-75
+    assert s.flat().shape == (13 * 12, 5)
+    assert (s.flat()[0] == s.M_1[0]).all() and (s.flat()[-1] == s.N_nj[4][-1]).all()
+
+
+def test_objective_invert_and_shapes():
+    s = saltelli.Sample(8, 23, lambda x: x, verbose=False)                         # test_objective.py:18-42
+    o = saltelli.Objective(8, 23, s, lambda x: 1.0 - x, verbose=False)
+    assert o.fM_1.shape == (23, 8) and o.fN_j.shape == (8, 23, 8)
+    assert abs(numpy.sum(1.0 - o.fM_1 - s.M_1)) < 1e-12 and abs(numpy.sum(1.0 - o.fN_nj - s.N_nj)) < 1e-9
+
+
+def test_varsens_value_error():
+    with pytest.raises(ValueError):
+        saltelli.Varsens(lambda x: 0.0)                                            # saltelli.py:556-559
+
+
+# ---- analytic acceptance (varsens/tests/test_g_function.py:52-73), via the chunked numpy path --
+def test_g_function_analytic_two_places():
+    k, n = 6, 1024 * 50
+    r = cport.run(k, n, cport.OBJ_GFUNCTION, A6)
+    var = float(r["var_y"][0])
+    assert abs(ob.g_var(A6) - var) < 5e-3 and abs(1.0 - float(r["E_2"][0])) < 5e-3
+    truth = ob.g_truth(A6)
+    for i in range(k):
+        assert abs(truth[i] - r["sens"][i, 0] * var) < 5e-3
+        assert abs(ob.g_truth_t(A6, i) - r["sens_t"][i, 0] * var) < 5e-3
+        for j in range(i + 1, k):
+            assert abs(ob.g_truth_2(A6, i, j) - r["sens_2"][i, 0, j, 0] * var) < 5e-3
+            assert abs(ob.g_truth_vnc(A6, [i, j]) - r["sens_2n"][i, 0, j, 0] * var) < 5e-3
+
+
+def test_g_truth_closed_forms_equal_subset_sums():
+    v = ob.g_truth(A6)
+    brute = sum(numpy.prod(v[list(m)]) for j in range(6) for m in itertools.combinations(range(6), j + 1))
+    assert abs(brute - ob.g_var(A6)) < 1e-15                                       # test_g_function.py:40-49
+    assert abs(ob.g_var(A6) - 0.5680709251532495) < 1e-15
+
+
+# ---- the three oracle forms agree with each other ---------------------------------------------
+def test_chunked_and_c_port_equal_literal(refgold):
+    p = pipeline.run(6, 1024, lambda x: x, lambda X: ob.g_function_rows(X, A6), chunk=300)
+    c = cport.run(6, 1024, cport.OBJ_GFUNCTION, A6)
+    for name in ("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t", "sens_2", "sens_2n"):
+        close(p[name], refgold["c1_" + name].reshape(p[name].shape))
+        close(c[name], refgold["c1_" + name].reshape(c[name].shape))
+
+
+def test_c_port_halton_and_flat_bit_exact(golden):
+    assert (cport.halton(20, 401, 64) == golden["halton_k20_first401"]).all()
+    assert (cport.halton(50, 1001, 16) == golden["halton_k50_first1001"]).all()
+    assert (cport.halton(20, 33554000, 16) == golden["halton_k20_first33554000"]).all()
+    assert (halton.halton_points(20, 33554000, 16) == golden["halton_k20_first33554000"]).all()
+    assert (cport.sample_flat(5, 13, discard=7) == golden["flat_k5_n13_identity_discard7"]).all()
+    lb, ub = golden["flat_k5_n13_linear_lb"], golden["flat_k5_n13_linear_ub"]
+    assert (cport.sample_flat(5, 13, scale=("linear", lb, ub)) == golden["flat_k5_n13_linear"]).all()
+    # any row window equals the same window of the whole
+    whole = cport.sample_flat(5, 13)
+    assert (cport.sample_flat(5, 13, row_begin=17, row_end=140) == whole[17:140]).all()
+
+
+def test_halton_first_points_and_goldens(golden):
+    h = halton.halton_points(5, 1, 3)
+    assert h[0].tolist() == [1 / 2, 1 / 3, 1 / 5, 1 / 7, 1 / 11]                   # ghalton's first get()
+    assert h[1, 0] == 0.25 and h[2, 0] == 0.75
+    assert halton.radical_inverse_scalar(1975, 2) == 0.92919921875                 # SURVEY App. A probe
+    assert (numpy.random.RandomState(1).permutation(1024)[:16] == golden["perm_1024_head"]).all()
+    # seed(1); shuffle(rows) == rows[RandomState(1).permutation(n)]   (saltelli.py:100-101)
+    m = numpy.arange(40.0).reshape(20, 2)
+    numpy.random.seed(1)
+    numpy.random.shuffle(m)
+    assert (m == numpy.arange(40.0).reshape(20, 2)[pipeline.permutation(20)]).all()
+
+
+def test_halton_term_table_sums_to_points():
+    bases, nd, off, terms = halton.halton_term_table(7, 100000)
+    for m in (1, 17, 4095, 99999, 100000):
+        for d, b in enumerate(bases):
+            x, mm = 0.0, m
+            for j in range(int(nd[d])):
+                x += terms[int(off[d]) + j * int(b) + mm % int(b)]
+                mm //= int(b)
+            assert x == halton.radical_inverse_scalar(m, int(b))
+
+
+def test_sobol_against_scipy_fixture(golden):
+    V = sobol.joe_kuo_direction_numbers(8)
+    assert (V == golden["sobol_joekuo_k8_dirnums"]).all()
+    assert (sobol.sobol_points(V, 4097, 32) == golden["sobol_joekuo_k8_from4097"]).all()
+    assert (sobol.sobol_points_sequential(V, 4097, 32) == golden["sobol_joekuo_k8_from4097"]).all()
+    assert sobol.quantize_6sig(golden["sobol_joekuo_k8_from4097"][0, 0]) == 0.500366   # SURVEY App. C probe
+
+
+def test_ishigami_analytic():
+    pi = math.pi
+    r = cport.run(3, 1 << 16, cport.OBJ_ISHIGAMI, [7.0, 0.1], scale=("linear", [-pi] * 3, [pi] * 3))
+    assert abs(r["var_y"][0] - 13.8446) < 0.15
+    for got, want in zip(r["sens"][:, 0], (0.3139, 0.4424, 0.0)):
+        assert abs(got - want) < 0.02
+    for got, want in zip(r["sens_t"][:, 0], (0.5576, 0.4424, 0.2437)):
+        assert abs(got - want) < 0.02
+    assert abs(r["sens_2"][0, 0, 2, 0] - 0.5576) < 0.03
