@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the Saltelli hot path (BASELINE.json metric: model evals/sec + index time).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole pipeline over the workload BASELINE.json's metric is quoted on:
+Sobol g-function, k=20, n=2^24 (704,643,072 evaluations), identity scaling, a=[0,.5,3,9,99,99]+[99]*14,
+fused generation + evaluation + reduction, second order included, GENERIC functor path (every point is
+evaluated; the separable prefix/suffix shortcut is reported separately under "separable_shortcut").
+N>1 shards the n base rows over ranks (total work fixed -> "strong"); one all-reduce of the partial sums.
+
+`value`   evals/s with the permutation already resident in HBM (device-timed, CUDA events, max over ranks).
+`e2e`     same metric through the public C-ABI call with HOST buffers: the permutation is copied from pinned
+          host memory and the indices are read back to the host inside the timed region, every step.
+`roofline` FP64-pipe roofline of the fused kernel: algorithmic flops (6008 per base row at k=20)
+          / kernel time (CUDA events around the launch, inside the library) / measured DFMA peak.
+`cpu_baseline` the oracle's vectorised numpy pipeline on all host cores, bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K = 20
+N_ROWS = 1 << 24
+A = [0, 0.5, 3, 9, 99, 99] + [99.0] * 14
+METRIC = "model evals/sec (Sobol g-function k=20 n=2^24, fused generation+evaluation+index estimation)"
+UNIT = "evals/s"
+
+
+def evals(n, k=K):
+    return 2 * n * (1 + k)
+
+
+def algorithmic_flops_per_row(k=K):
+    # 5k per evaluation x 2(1+k) evaluations + (8k+8) first order + (4k^2+2k) second order
+    return 2 * (1 + k) * 5 * k + (8 * k + 8) + (4 * k * k + 2 * k)
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's numpy pipeline (BASELINE.md §3.2 "CPU numpy") on all host cores
+# -------------------------------------------------------------------------------------------------
+_POOL_STATE = {}
+
+
+def _cpu_chunk(args):
+    from oracle import pipeline, objectives
+    i0, i1 = args
+    st = _POOL_STATE
+    S = pipeline.run(K, st["n"], lambda x: x, lambda X: objectives.g_function_rows(X, A), i0=i0, i1=i1,
+                     perm=st["perm"], chunk=1 << 14, acc_dtype=numpy.float64, finalize=False)
+    return S
+
+
+def cpu_numpy_evals_per_s(target_seconds=12.0, cores=None):
+    """Times the vectorised numpy oracle on a bounded sample of the C3 workload (same n, same permutation, the
+    first `rows` base rows).  Returns (evals/s, cores, sample description)."""
+    import multiprocessing as mp
+    from oracle import pipeline
+    cores = cores or os.cpu_count() or 1
+    _POOL_STATE["n"] = N_ROWS
+    if "perm" not in _POOL_STATE:
+        _POOL_STATE["perm"] = pipeline.permutation(N_ROWS)
+    ctx = mp.get_context("fork")
+    per_task = 1 << 14
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()                                     # calibration: one task per core
+        pool.map(_cpu_chunk, [(c * per_task, (c + 1) * per_task) for c in range(cores)])
+        cal = time.perf_counter() - t0
+        rate = cores * per_task / cal                                # rows/s
+        rows = int(min(N_ROWS, max(cores * per_task, rate * target_seconds)))
+        rows = (rows // (cores * per_task)) * cores * per_task or cores * per_task
+        tasks = [(i, i + per_task) for i in range(0, rows, per_task)]
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, tasks)
+        dt = time.perf_counter() - t0
+    return evals(rows) / dt, cores, "first %d of %d base rows (%d evals), numpy float64 sums, %d processes" % (
+        rows, N_ROWS, evals(rows), cores), dt
+
+
+def cpu_extras():
+    """Two more CPU numbers for context: the C/OpenMP port and the literal per-row Python loop."""
+    from oracle import cport, saltelli, objectives
+    out = {}
+    n_s = 1 << 18
+    t0 = time.perf_counter()
+    cport.sums(K, N_ROWS, cport.OBJ_GFUNCTION, A, i0=0, i1=n_s)
+    out["c_openmp_port_evals_per_s"] = evals(n_s) / (time.perf_counter() - t0)
+    out["c_openmp_threads"] = int(cport.lib().orc_num_threads())
+    n_l = 128
+    t0 = time.perf_counter()
+    s = saltelli.Sample(K, n_l, lambda x: x, verbose=False)
+    o = saltelli.Objective(K, n_l, s, lambda x: objectives.g_function_row(x, A), verbose=False)
+    saltelli.Varsens(o, verbose=False)
+    out["literal_python_loop_evals_per_s"] = evals(n_l) / (time.perf_counter() - t0)
+    return out
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference cannot run here (Python 2, ghalton absent), so this times the oracle port
+    of its pipeline -- vectorised numpy on every host core -- on bounded samples of the same workload."""
+    if rank != 0:
+        return
+    vals, sample = [], ""
+    for it in range(args.warmup + args.steps):
+        v, cores, sample, dt = cpu_numpy_evals_per_s(target_seconds=8.0)
+        if it >= args.warmup:
+            vals.append((v, dt))
+    value = float(numpy.mean([v for v, _ in vals]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(numpy.mean([d for _, d in vals])), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 g-function k=20 n=2^24 (bounded sample per step)", "k": K, "n": N_ROWS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(numpy.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import varsens_b200 as vb
+    from varsens_b200 import _cabi, dist as vdist
+    from oracle import pipeline
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = vb.Context.get(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    n, k = N_ROWS, K
+    flags = _cabi.FLAG_SECOND_ORDER
+    perm_host = torch.from_numpy(pipeline.permutation(n).astype(numpy.int32)).pin_memory()   # reference's own RNG, saltelli.py:100-101
+    perm_dev = perm_host.to(dev)
+    lo, hi = vdist.shard_range(n, rank, world)
+    plen = vdist.partials_layout(k)["length"]
+    part = torch.zeros(plen, dtype=torch.float64, device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step_resident():
+        ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
+        vdist.allreduce_partials(part)
+        return ctx.finalize(k, 1, n, part, flags)
+
+    def step_e2e():
+        # public call with HOST buffers: permutation slice H2D from pinned memory, indices D2H, every step
+        if world == 1:
+            return ctx.run_fused(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, flags=flags)
+        ctx.fused_partials(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
+        vdist.allreduce_partials(part)
+        return ctx.finalize(k, 1, n, part, flags)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, kernel_ms=None):
+        for _ in range(warmup):
+            fn()
+            flush.zero_()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()                                               # L2 flush between timed iterations
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            res = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            dev_ms = e0.elapsed_time(e1)
+            tot += max(dev_ms, wall) if fn is step_e2e else dev_ms      # e2e includes the host-side call/return
+            if kernel_ms is not None:
+                kernel_ms.append(ctx.last_kernel_ms())
+        barrier()
+        t = torch.tensor([tot / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), res
+
+    peak_tflops = ctx.measure_fp64_peak()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launch_count()
+    kernel_ms = []
+    ms, res = timed(step_resident, args.steps, args.warmup, kernel_ms)
+    launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3))
+
+    # fused kernel alone (this rank's shard), separable shortcut for context
+    sep_ms = None
+    if world == 1:
+        ms_sep, _ = timed(lambda: ctx.run_fused(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A,
+                                                flags=flags | _cabi.FLAG_SEPARABLE), max(2, args.steps // 2), 2)
+        sep_ms = ms_sep
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    kms = float(numpy.mean(kernel_ms))
+    rows_rank0 = hi - lo
+    flops = algorithmic_flops_per_row(k) * rows_rank0
+    achieved = flops / (kms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": evals(n) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 Sobol g-function k=20 n=2^24 identity scaling, fused generic functor, second order on",
+                   "k": k, "n": n, "evals_per_step": evals(n), "parallelism": "rows sharded over %d rank(s), 1 all-reduce of %d doubles" % (world, plen),
+                   "l2": "192 MiB buffer written between timed iterations (L2 flush)", "index_time_ms": "included (finalize kernel + D2H of %d doubles)" % (6 * k + 2 + 2 * k * k)},
+        "e2e": {"value": evals(n) / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k))},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                     "traffic": None, "kernel": "vs::fused_kernel<20, GFunctionReg<20>, true, false>", "kernel_ms": kms,
+                     "algorithmic_flops_per_launch": flops,
+                     "peak_source": "DFMA-chain microbenchmark run in this process (vs_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"},
+        "clocks": clocks,
+        "check": {"var_y": float(res.var_y[0]), "E_2": float(res.E_2[0]), "sens0": float(res.sens[0, 0]),
+                  "e2e_equals_resident": bool(numpy.array_equal(res.sens, res2.sens))},
+    }
+    if sep_ms is not None:
+        line["separable_shortcut"] = {"value": evals(n) / (sep_ms * 1e-3), "unit": UNIT, "ms_per_step": sep_ms,
+                                      "note": "prefix/suffix products (VS_FLAG_SEPARABLE); not used for value/roofline"}
+    if world == 1 and not args.no_cpu:
+        v, cores, sample, _ = cpu_numpy_evals_per_s(target_seconds=12.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"].update(cpu_extras())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3
+    run_gpu(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

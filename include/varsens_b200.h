@@ -1,0 +1,169 @@
+/* varsens_b200 -- C ABI of the B200-native Saltelli hot path (libvarsens_b200.so).
+ *
+ * The reference (LoLab-MSM/varsens) has no FFI: its boundary is the Python API of
+ * varsens/saltelli.py and varsens/scale.py.  Every entry point below names the reference code it
+ * replaces (file:line under the reference checkout); varsens_b200/saltelli.py is the host mirror
+ * that binds them through ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain C symbols, int status return (VS_OK == 0), no exceptions cross the ABI;
+ *    vs_last_error() returns the thread-local message of the last failing call.
+ *  - the CALLER owns every data buffer.  Each buffer argument is paired with a VS_MEM_* flag:
+ *    VS_MEM_DEVICE = device pointer on the ctx's GPU (e.g. torch.Tensor.data_ptr()),
+ *    VS_MEM_HOST   = host pointer (numpy); the library stages it through its own device scratch
+ *    with cudaMemcpyAsync on the ctx stream (pinned host memory makes that copy asynchronous).
+ *  - small descriptor arguments (vs_scale bounds, objective parameters, direction numbers,
+ *    vs_result arrays) are always HOST memory.
+ *  - one in-flight call per ctx; calls are issued on the ctx stream and return after the stream
+ *    has been synchronised unless the output is VS_MEM_DEVICE (then the work is only enqueued).
+ *  - everything is IEEE fp64; indices are uint64 in the ABI (Halton index of any generated point
+ *    must stay below 2^32: VS_ERR_RANGE otherwise).
+ *  - there is NO CPU fallback: without a CUDA device vs_ctx_create fails with VS_ERR_CUDA.
+ */
+#ifndef VARSENS_B200_H
+#define VARSENS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_ABI_VERSION 1
+
+typedef struct vs_ctx vs_ctx;
+
+enum vs_status { VS_OK = 0, VS_ERR_ARG = 1, VS_ERR_CUDA = 2, VS_ERR_RANGE = 3, VS_ERR_NOMEM = 4, VS_ERR_UNSUPPORTED = 5 };
+enum vs_mem { VS_MEM_HOST = 0, VS_MEM_DEVICE = 1 };
+
+/* varsens/scale.py: identity (lambda x: x), linear (:33), power (:62).  percentage (:90-91) lowers
+ * to linear and magnitude (:121-122) to power on the host, exactly as scale.py does. */
+enum vs_scale_kind { VS_SCALE_IDENTITY = 0, VS_SCALE_LINEAR = 1, VS_SCALE_POWER = 2 };
+typedef struct vs_scale {
+    int kind;
+    const double *lower; /* host, k doubles (ignored for identity) */
+    const double *upper; /* host, k doubles */
+} vs_scale;
+
+/* Registered device objective functors (the reference calls a Python callable once per row,
+ * varsens/saltelli.py:308-353).  params are host doubles:
+ *   GFUNCTION  : a[0..k)                      f = prod_c (|4 x_c - 2| + a_c) / (1 + a_c)
+ *                (varsens/tests/test_g_function.py:9-13, README.md:33-36)
+ *   ISHIGAMI   : {A, B}, k >= 3               f = sin x0 + A sin^2 x1 + B x2^4 sin x0
+ *   RK4_CHAIN  : {dt, nsteps}, k even         reversible mass-action chain X_0 <-> ... <-> X_{k/2},
+ *                forward rates x[0..k/2), reverse rates x[k/2..k), X(0) = e_0, classic RK4,
+ *                f = X_{k/2}(nsteps*dt)       (spec frozen in oracle/objectives.py) */
+enum vs_objective { VS_OBJ_GFUNCTION = 0, VS_OBJ_ISHIGAMI = 1, VS_OBJ_RK4_CHAIN = 2 };
+
+enum vs_flags {
+    VS_FLAG_SECOND_ORDER = 1, /* also accumulate the k x k Grams for sens_2 / sens_2n */
+    VS_FLAG_SEPARABLE = 2     /* product-form objectives only: evaluate the 2+2k points of a row from
+                                 prefix/suffix products (O(k) instead of O(k^2)); reported separately,
+                                 never used for the roofline figure */
+};
+
+/* Results of varsens/saltelli.py:572-622, host arrays the caller allocates (row-major):
+ * E_2[l], var_y[l], U_j[k][l], U_nj[k][l], sens[k][l], sens_t[k][l], sens_2[k][l][k][l],
+ * sens_2n[k][l][k][l].  sens_2 / sens_2n may be NULL when second order was not requested. */
+typedef struct vs_result {
+    double *E_2, *var_y, *U_j, *U_nj, *sens, *sens_t, *sens_2, *sens_2n;
+} vs_result;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int vs_abi_version(void);
+const char *vs_last_error(void);
+int vs_ctx_create(int device, vs_ctx **out);
+int vs_ctx_destroy(vs_ctx *ctx);
+/* Run on a caller stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
+int vs_ctx_set_stream(vs_ctx *ctx, void *cuda_stream);
+int vs_ctx_synchronize(vs_ctx *ctx);
+/* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
+uint64_t vs_ctx_launch_count(const vs_ctx *ctx);
+
+/* ---- host-only helpers (no GPU needed) ----------------------------------------------------- */
+/* ghalton's bases: the first k primes (call site varsens/saltelli.py:82). */
+int vs_halton_bases(int k, uint32_t *bases);
+/* The per-digit term table the kernels sum in order: terms[offsets[d] + j*bases[d] + digit] =
+ * digit / bases[d]^(j+1), j < ndigits[d] = #digits of max_index in base d.  Pass terms == NULL to
+ * query *count.  This single function fixes the generator's fp64 arithmetic (swap it to re-point
+ * the kernels at a different ghalton build). */
+int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offsets, double *terms,
+                    uint64_t capacity, uint64_t *count);
+/* Length of the partial-sum vector for k factors and l outputs: 4l + m(m+1)/2, m = (2+2k) l.
+ * Layout: S_A[l], S_B[l], Q_A[l], Q_B[l] (sums / sums of squares of fM_1 - c, fM_2 - c for a
+ * common shift c), then the upper triangle (row-major, t <= u) of G[t][u] = sum_i v_i[t] v_i[u]
+ * with v_i = (fM_1[i], fM_2[i], fN_j[0..k)[i], fN_nj[0..k)[i]) x outputs, index t*l + o. */
+size_t vs_partials_len(int k, int l);
+
+/* ---- generators ---------------------------------------------------------------------------- */
+/* ghalton.Halton(k).get() points of 1-based indices first_index .. first_index+count-1, scaled;
+ * out is row-major (count, k).  Replaces varsens/saltelli.py:82-84 (+ :92,95 scaling). */
+int vs_halton(vs_ctx *ctx, int k, uint64_t first_index, uint64_t count, const vs_scale *scale,
+              double *out, int out_mem);
+/* 32-bit Gray-code Sobol points first_point .. first_point+count-1 (point 0 = origin) by direct
+ * indexing; dirnums is host uint32 [k][32], MSB-aligned.  quantize6 != 0 reproduces the 6
+ * significant decimal digits sobolGen prints.  Replaces quantlib/sobolGen.cpp:47-63
+ * (row r of its output is point 4097 + r). */
+int vs_sobol(vs_ctx *ctx, int k, uint64_t first_point, uint64_t count, const uint32_t *dirnums,
+             int quantize6, const vs_scale *scale, double *out, int out_mem);
+
+/* ---- sample assembly (export mode) ----------------------------------------------------------- */
+/* Rows [row_begin,row_end) of Sample.flat() -- M_1 | M_2 | N_j[0..k) | N_nj[0..k), each n rows --
+ * written row-major (row_end-row_begin, k).  perm = the row permutation of M_2 (n uint32).
+ * raw == NULL: Halton source with s = 20k + discard points skipped.  raw != NULL: an unscaled
+ * (2n,k) sample (Sample(raw=...) / loadFile=..., e.g. Sobol).  Replaces varsens/saltelli.py:86-125
+ * (scale, shuffle, generate_N_j) and :127-160 (flat). */
+int vs_sample_flat(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                   const double *raw, int raw_mem, const vs_scale *scale, uint64_t row_begin,
+                   uint64_t row_end, double *out, int out_mem);
+
+/* ---- objective evaluation --------------------------------------------------------------------- */
+/* Objective values of base rows [i_begin,i_end) for a registered functor, sample rows generated on
+ * the fly (never stored): fvals[(t*rows + (i-i_begin))], t in [0,2+2k), rows = i_end-i_begin --
+ * for the full range this is Objective.flat().  Replaces varsens/saltelli.py:308-353. */
+int vs_eval_values(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                   const double *raw, int raw_mem, const vs_scale *scale, int objective,
+                   const double *params, int n_params, uint64_t i_begin, uint64_t i_end, double *fvals,
+                   int fvals_mem);
+
+/* ---- estimators --------------------------------------------------------------------------------- */
+/* Partial sums (vs_partials_len doubles) of `rows` base rows of objective values laid out
+ * fvals[(t*rows + r)*l + o].  shift = host l doubles (common shift c, must be identical on every
+ * rank; NULL = 0).  Replaces the reductions of varsens/saltelli.py:577-622. */
+int vs_partials_from_values(vs_ctx *ctx, int k, int l, uint64_t rows, const double *fvals, int fvals_mem,
+                            const double *shift, int flags, double *partials, int partials_mem);
+/* Indices from (all-reduced) partial sums; n = the reference's divisor (saltelli.py:577,591-596). */
+int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, const double *partials, int partials_mem, int flags,
+                vs_result *result);
+/* vs_partials_from_values + vs_finalize over a whole design (Objective(objective_vals=...) route,
+ * varsens/saltelli.py:297-298 -> :572-622).  rows may be < n after NaN trimming (:474-495). */
+int vs_indices_from_values(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *fvals,
+                           int fvals_mem, int flags, vs_result *result);
+
+/* ---- fused pipeline ------------------------------------------------------------------------------ */
+/* Generation + scaling + assembly + objective + reductions for base rows [i_begin,i_end) in one
+ * kernel; sample matrices never touch HBM.  Produces this shard's partial sums; sum them over
+ * ranks (one all-reduce) and call vs_finalize.  Replaces varsens/saltelli.py:82-125, :308-353 and
+ * the reductions of :577-622. */
+int vs_fused_partials(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                      const double *raw, int raw_mem, const vs_scale *scale, int objective,
+                      const double *params, int n_params, uint64_t i_begin, uint64_t i_end, int flags,
+                      double *partials, int partials_mem);
+/* Single-GPU convenience: vs_fused_partials over [0,n) + vs_finalize.  This is
+ * Varsens(objective, scaling, k, n) (varsens/saltelli.py:545-570) for a registered functor. */
+int vs_run_fused(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                 const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                 int n_params, int flags, vs_result *result);
+
+/* ---- measurement helpers --------------------------------------------------------------------------- */
+/* DFMA-chain microbenchmark: returns measured FP64 TFLOP/s (FMA = 2 flops) of this GPU in *tflops. */
+int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops);
+/* Device time in ms of the last vs_fused_partials / vs_eval_values / vs_partials_from_values /
+ * vs_sample_flat main kernel, from CUDA events recorded on the ctx stream. */
+int vs_last_kernel_ms(vs_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VARSENS_B200_H */

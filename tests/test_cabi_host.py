@@ -1,0 +1,155 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol the header declares,
+its host-side tables equal the oracle's, and the host mirror's pure-Python logic (scale tracing,
+sharding, the N>1 all-reduce plumbing over gloo) works.  No GPU compute is called here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from oracle import halton as ohalton, pipeline, cport, objectives as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    import __graft_entry__ as g
+    g.build()
+    from varsens_b200 import _cabi
+    return _cabi
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    header = open(os.path.join(ROOT, "include", "varsens_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(vs_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(cabi.SYMBOLS)
+    lib = cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vs_abi_version() == 1
+
+
+def test_halton_term_table_equals_oracle(cabi):
+    for k, mx in ((1, 10), (6, 121 + 2048), (20, 401 + 2 ** 25), (50, 1001 + 2 ** 23)):
+        b, nd, off, t = cabi.halton_terms(k, mx)
+        ob_, ond, ooff, ot = ohalton.halton_term_table(k, mx)
+        assert (b == ob_).all() and (nd == ond).all() and (off == ooff).all()
+        assert t.shape == ot.shape and (t == ot).all()
+    assert cabi.halton_terms(20, 401 + 2 ** 25)[3].size == 3523          # SURVEY §7 probe
+
+
+def test_partials_len(cabi):
+    from varsens_b200 import dist
+    for k, l in ((1, 1), (6, 1), (20, 1), (6, 2), (50, 3)):
+        m = (2 + 2 * k) * l
+        assert cabi.lib().vs_partials_len(k, l) == 4 * l + m * (m + 1) // 2 == dist.partials_layout(k, l)["length"]
+
+
+def test_no_cpu_fallback(cabi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cabi.VarsensError, match="no CPU fallback"):
+        cabi.Context(0)
+    import varsens_b200 as vb
+    with pytest.raises(cabi.VarsensError):
+        vb.Varsens(vb.GFunction([0.0, 1.0]), lambda x: x, 2, 8, verbose=False)
+    with pytest.raises(cabi.VarsensError, match="device functor"):
+        vb.GFunction([0.0])(numpy.zeros(1))
+
+
+def test_scale_helpers_match_reference_numbers(refgold):
+    from varsens_b200 import scale
+    p = refgold["scale_p"]
+    assert (scale.linear(p, -3.5, 12.25) == refgold["scale_linear"]).all()
+    assert (scale.power(p, 0.01, 250.0) == refgold["scale_power"]).all()
+    assert (scale.percentage(p, 40.0, 33.0) == refgold["scale_percentage"]).all()
+    assert (scale.magnitude(p, 2.5, 2.0, 10.0) == refgold["scale_magnitude"]).all()
+    import varsens_b200 as vb
+    assert vb.linear is scale.linear and vb.magnitude is scale.magnitude          # star export, __init__.py:2
+
+
+def test_scale_tracing(cabi):
+    from varsens_b200 import scale
+    lb, ub = numpy.array([-1.0, 2.0, 3.0]), numpy.array([1.0, 4.0, 30.0])
+    d = scale.trace(lambda x: x, 3)
+    assert d.kind == cabi.SCALE_IDENTITY
+    d = scale.trace(lambda x: scale.linear(x, lb, ub), 3)
+    assert d.kind == cabi.SCALE_LINEAR and (d.lower == lb).all() and (d.upper == ub).all()
+    d = scale.trace(lambda x: scale.percentage(x, ub, 33.0), 3)
+    assert d.kind == cabi.SCALE_LINEAR and numpy.allclose(d.lower, ub * 0.67)
+    d = scale.trace(lambda x: scale.magnitude(x, ub, orders=1.0), 3)
+    assert d.kind == cabi.SCALE_POWER and (d.lower == ub / 10.0).all() and (d.upper == ub * 10.0).all()
+    d = scale.trace(lambda x: scale.linear(x, -numpy.pi, numpy.pi), 3)            # scalar bounds broadcast
+    assert d.kind == cabi.SCALE_LINEAR and d.lower.shape == (3,)
+    assert scale.trace(lambda x: scale.linear(x, lb, ub) + 1.0, 3) is None       # not a pure scale.* call
+    assert scale.trace(lambda x: x * 2.0, 3) is None
+    assert scale.trace(lambda x: numpy.sqrt(x), 3) is None
+
+
+def test_shard_range_partitions():
+    from varsens_b200 import dist
+    for total in (0, 1, 7, 1024, 2 ** 24 + 5):
+        for ws in (1, 2, 3, 8):
+            edges = [dist.shard_range(total, r, ws) for r in range(ws)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        dist.shard_range(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys, numpy, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from varsens_b200 import dist as vdist
+from oracle import cport, pipeline
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+k, n = 6, 1000
+a = [0, .5, 3, 9, 99, 99]
+rank, ws = vdist.world()
+lo, hi = vdist.shard_range(n, rank, ws)
+S = cport.sums(k, n, cport.OBJ_GFUNCTION, a, i0=lo, i1=hi)           # this rank's shard, oracle arithmetic
+lay = vdist.partials_layout(k)
+p = numpy.zeros(lay["length"])
+m, J, N = lay["m"], range(2, 2 + k), range(2 + k, 2 + 2 * k)
+g = lay["gram"]
+p[lay["S_A"]], p[lay["S_B"]], p[lay["Q_A"]], p[lay["Q_B"]] = S["s_a"], S["s_b"], S["q_a"], S["q_b"]
+p[g(0, 1)] = S["s_ab"]; p[g(0, 0)] = S["q_a"]; p[g(1, 1)] = S["q_b"]
+for j in range(k):
+    p[g(0, 2 + j)], p[g(1, 2 + k + j)], p[g(0, 2 + k + j)], p[g(1, 2 + j)] = S["aJ"][j], S["bN"][j], S["aN"][j], S["bJ"][j]
+    for i in range(k):
+        p[g(2 + k + i, 2 + j)] = S["NJ"][i, j]
+        if i <= j:
+            p[g(2 + k + i, 2 + k + j)] = S["NN"][i, j]; p[g(2 + i, 2 + j)] = S["JJ"][i, j]
+t = torch.from_numpy(p)
+vdist.allreduce_partials(t)
+if rank == 0:
+    whole = cport.sums(k, n, cport.OBJ_GFUNCTION, a)
+    q = t.numpy()
+    assert abs(q[g(0, 1)] - float(whole["s_ab"])) < 1e-9
+    assert abs(q[g(2 + k + 1, 2 + 3)] - float(whole["NJ"][1, 3])) < 1e-9
+    assert abs(q[lay["S_A"]] + q[lay["S_B"]] - float(whole["s_a"] + whole["s_b"])) < 1e-9
+    print("GLOO_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_allreduce_over_gloo(tmp_path):
+    """world_size-2 run of the N>1 host path on CPU: shard ranges, partial-vector layout, one all-reduce."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GLOO_OK" in outs[0]

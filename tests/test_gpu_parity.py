@@ -1,0 +1,450 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the host mirror) against the CPU oracle and the
+golden fixtures.  Bit-exact for generated points and assembled sample matrices (identity / linear
+scaling); <= 2 ulp for power scaling (libm pow is platform-defined); indices within
+1e-10 relative or 1e-12 absolute (BASELINE.json)."""
+import math
+
+import numpy
+import pytest
+
+from conftest import close
+from oracle import cport, halton as ohalton, objectives as ob, pipeline, saltelli as osalt, scale as oscale, sobol as osobol
+
+pytestmark = pytest.mark.gpu
+
+A6 = [0, 0.5, 3, 9, 99, 99]
+A20 = A6 + [99.0] * 14
+NAMES = ("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t", "sens_2", "sens_2n")
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import varsens_b200
+    return varsens_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(vb):
+    return vb.Context.get(0)
+
+
+def perm_of(n):
+    return pipeline.permutation(n).astype(numpy.uint32)
+
+
+def ulp_diff(a, b):
+    a, b = numpy.asarray(a, dtype=numpy.float64), numpy.asarray(b, dtype=numpy.float64)
+    return numpy.abs(a.view(numpy.int64) - b.view(numpy.int64)).max()
+
+
+def assert_indices(res, ref, names=NAMES):
+    for name in names:
+        close(numpy.asarray(getattr(res, name)).reshape(ref[name].shape), ref[name])
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 Halton
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,first,count", [(1, 1, 1), (6, 121, 2048), (20, 401, 5000), (50, 1001, 777),
+                                           (20, 33554000, 900), (3, 4294960000, 5000), (97, 1, 64)])
+def test_halton_bit_exact(ctx, k, first, count):
+    got = ctx.halton(k, first, count)
+    assert (got == cport.halton(k, first, count)).all()
+
+
+def test_halton_golden(ctx, golden):
+    assert (ctx.halton(20, 401, 64) == golden["halton_k20_first401"]).all()
+    assert (ctx.halton(50, 1001, 16) == golden["halton_k50_first1001"]).all()
+    assert (ctx.halton(20, 33554000, 16) == golden["halton_k20_first33554000"]).all()
+    assert ctx.halton(5, 1, 1)[0].tolist() == [1 / 2, 1 / 3, 1 / 5, 1 / 7, 1 / 11]
+
+
+def test_halton_scaled_and_edges(ctx, vb):
+    from varsens_b200 import _cabi
+    lb, ub = numpy.linspace(-5, 3, 7), numpy.linspace(4, 90, 7)
+    got = ctx.halton(7, 141, 1000, _cabi.Scale(_cabi.SCALE_LINEAR, lb, ub))
+    assert (got == oscale.linear(ohalton.halton_points(7, 141, 1000), lb, ub)).all()
+    lo, up = numpy.linspace(0.01, 3, 7), numpy.linspace(4, 9000, 7)
+    got = ctx.halton(7, 141, 1000, _cabi.Scale(_cabi.SCALE_POWER, lo, up))
+    assert ulp_diff(got, oscale.power(ohalton.halton_points(7, 141, 1000), lo, up)) <= 2     # tolerance: 2 ulp
+    assert ctx.halton(4, 10, 0).shape == (0, 4)                                    # empty
+    with pytest.raises(vb.VarsensError):
+        ctx.halton(4, 2 ** 32 - 10, 100)                                           # index range
+    with pytest.raises(vb.VarsensError):
+        ctx.halton(4, 0, 1)                                                        # indices are 1-based
+
+
+def test_halton_device_output(ctx):
+    import torch
+    out = torch.empty((3000, 20), dtype=torch.float64, device="cuda:0")
+    ctx.halton(20, 401, 3000, out=out)
+    ctx.synchronize()
+    assert (out.cpu().numpy() == cport.halton(20, 401, 3000)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 Sobol
+# ------------------------------------------------------------------------------------------------
+def test_sobol_skip_ahead(ctx, golden):
+    V = golden["sobol_joekuo_k8_dirnums"]
+    assert (ctx.sobol(8, 4097, 32, V) == golden["sobol_joekuo_k8_from4097"]).all()
+    V50 = osobol.joe_kuo_direction_numbers(50)
+    for first, count in ((0, 1000), (4097, 3000), (2 ** 31 - 7, 100), (2 ** 32 - 500, 500)):
+        assert (ctx.sobol(50, first, count, V50) == osobol.sobol_points(V50, first, count)).all()
+    q = ctx.sobol(50, 4097, 2000, V50, quantize6=True)
+    assert (q == osobol.quantize_6sig(osobol.sobol_points(V50, 4097, 2000))).all()   # sobolGen.cpp:59 round trip
+    assert q[0, 0] == 0.500366
+    q = ctx.sobol(3, 1, 70000, V50[:3], quantize6=True)                               # tiny values, e-notation
+    assert (q == osobol.quantize_6sig(osobol.sobol_points(V50[:3], 1, 70000))).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 sample assembly / export mode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,n,discard", [(1, 2, 0), (3, 5, 0), (5, 13, 7), (6, 1024, 0), (20, 333, 11), (50, 100, 0),
+                                         (130, 9, 3)])
+def test_sample_flat_identity_bit_exact(ctx, k, n, discard):
+    got = ctx.sample_flat(k, n, perm_of(n), discard)
+    assert (got == cport.sample_flat(k, n, discard)).all()
+
+
+def test_sample_flat_goldens(ctx, golden, refgold):
+    assert (ctx.sample_flat(5, 13, perm_of(13), 7) == golden["flat_k5_n13_identity_discard7"]).all()
+    from varsens_b200 import _cabi
+    lin = _cabi.Scale(_cabi.SCALE_LINEAR, refgold["lin_lb"], refgold["lin_ub"])
+    assert (ctx.sample_flat(5, 13, perm_of(13), 7, lin) == refgold["lin_flat_k5_n13_discard7"]).all()
+    f = ctx.sample_flat(6, 1024, perm_of(1024))
+    assert (f[:8] == refgold["c1_flat_head"]).all() and (f[-8:] == refgold["c1_flat_tail"]).all()
+    assert (f[refgold["c1_flat_rows_probe"]] == refgold["c1_flat_probe"]).all()
+    ref = refgold["mag_ref"]
+    mag = _cabi.Scale(_cabi.SCALE_POWER, ref / 10.0, ref * 10.0)
+    assert ulp_diff(ctx.sample_flat(4, 9, perm_of(9), 0, mag), refgold["mag_flat_k4_n9"]) <= 2   # tolerance: 2 ulp
+    raw = refgold["raw_in"]
+    lin = _cabi.Scale(_cabi.SCALE_LINEAR, numpy.full(4, -1.0), numpy.full(4, 2.0))
+    assert (ctx.sample_flat(4, 10, perm_of(10), 0, lin, raw=raw) == refgold["raw_flat_k4_n10"]).all()
+
+
+def test_sample_flat_windows_and_device_buffers(ctx):
+    import torch
+    k, n = 7, 1000
+    whole = cport.sample_flat(k, n, 5)
+    total = 2 * n * (1 + k)
+    perm_dev = torch.from_numpy(perm_of(n).astype(numpy.int32)).cuda()
+    for lo, hi in ((0, total), (0, 1), (total - 1, total), (17, 18), (999, 1001), (1990, 2050), (2500, 12345),
+                   (3, total - 3), (100, 100)):
+        out = torch.full((hi - lo, k), -7.0, dtype=torch.float64, device="cuda:0")
+        ctx.sample_flat(k, n, perm_dev, 5, row_begin=lo, row_end=hi, out=out)
+        ctx.synchronize()
+        assert (out.cpu().numpy() == whole[lo:hi]).all(), (lo, hi)
+    with pytest.raises(Exception):
+        ctx.sample_flat(k, n, perm_of(n), 5, row_begin=5, row_end=total + 1)
+
+
+def test_sample_flat_large_property(ctx):
+    """Structure at a size the oracle cannot hold (k=50, n=2^16 -> 2.7 GB on device): column-substitution
+    identities of saltelli.py:119-123 checked on the device with torch, plus a checksum of checksums."""
+    import torch
+    k, n = 50, 1 << 16
+    out = torch.empty((2 * n * (1 + k), k), dtype=torch.float64, device="cuda:0")
+    ctx.sample_flat(k, n, perm_of(n), out=out)
+    ctx.synchronize()
+    M1, M2 = out[:n], out[n:2 * n]
+    NJ = out[2 * n:2 * n + k * n].view(k, n, k)
+    NN = out[2 * n + k * n:].view(k, n, k)
+    for j in (0, 1, 17, 49):
+        expect = M2.clone()
+        expect[:, j] = M1[:, j]
+        assert torch.equal(NJ[j], expect)
+        expect = M1.clone()
+        expect[:, j] = M2[:, j]
+        assert torch.equal(NN[j], expect)
+    # every block sums to (k-1) columns of one matrix + 1 column of the other
+    c1, c2 = M1.sum(0), M2.sum(0)
+    tot = out.sum(0)
+    want = (1 + k) * (c1 + c2)
+    assert torch.allclose(tot, want, rtol=1e-12)
+    head = cport.sample_flat(k, n, row_begin=n - 3, row_end=n + 5)
+    assert (out[n - 3:n + 5].cpu().numpy() == head).all()
+    assert float(out.min()) > 0.0 and float(out.max()) < 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# estimators on given values
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,n,l", [(1, 2, 1), (3, 50, 1), (6, 1024, 1), (6, 256, 2), (20, 4096, 1), (50, 600, 1),
+                                   (10, 333, 3), (100, 70, 1)])
+def test_indices_from_values(ctx, k, n, l):
+    rng = numpy.random.RandomState(k * 1000 + n + l)
+    vals = rng.rand(2 * n * (1 + k), l) * 3.0 + 10.0
+    o = osalt.Objective(k, n, objective_vals=vals, verbose=False)
+    v = osalt.Varsens(o, verbose=False)
+    res = ctx.indices_from_values(k, l, n, n, vals)
+    for name in NAMES:
+        close(getattr(res, name), numpy.asarray(getattr(v, name)).reshape(getattr(res, name).shape), rel=1e-10, abs_=1e-9)
+
+
+def test_indices_from_values_reference_goldens(ctx, refgold):
+    res = ctx.indices_from_values(6, 1, 1024, 1024, refgold["c1_obj_flat"])
+    for name in NAMES:
+        close(getattr(res, name), refgold["c1_" + name].reshape(getattr(res, name).shape))
+    res = ctx.indices_from_values(6, 2, 256, 256, refgold["two_obj_flat"])
+    for name in NAMES:
+        close(getattr(res, name), refgold["two_" + name].reshape(getattr(res, name).shape))
+
+
+def test_partials_shards_sum_to_whole(ctx):
+    k, n = 6, 1000
+    vals = cport.values(k, n, cport.OBJ_GFUNCTION, A6)                      # (2+2k, n)
+    whole = ctx.partials_from_values(k, 1, n, vals, shift=[vals[0, 0]])
+    acc = numpy.zeros_like(whole)
+    for lo, hi in ((0, 333), (333, 334), (334, 1000)):
+        acc += ctx.partials_from_values(k, 1, hi - lo, numpy.ascontiguousarray(vals[:, lo:hi]), shift=[vals[0, 0]])
+    numpy.testing.assert_allclose(acc, whole, rtol=1e-13, atol=1e-12)
+    res = ctx.finalize(k, 1, n, acc)
+    assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, A6))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused pipeline
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,n", [(2, 2), (2, 33), (3, 1000), (4, 64), (5, 31), (6, 1024), (8, 500), (10, 999), (12, 256),
+                                 (16, 77), (20, 4096), (7, 300), (24, 200)])
+def test_fused_gfunction_matches_oracle(ctx, k, n):
+    a = (A20 + [1.0, 2.0, 5.0, 99.0])[:k]
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, a)          # k=7, 24: two-phase path inside the library
+    assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, a))
+
+
+def test_fused_c1_reference_golden(ctx, refgold):
+    res = ctx.run_fused(6, 1024, perm_of(1024), cport.OBJ_GFUNCTION, A6)
+    for name in NAMES:
+        close(getattr(res, name), refgold["c1_" + name].reshape(getattr(res, name).shape))
+
+
+def test_fused_variants_agree(ctx):
+    from varsens_b200 import _cabi
+    k, n = 20, 5000
+    p = perm_of(n)
+    ref = cport.run(k, n, cport.OBJ_GFUNCTION, A20)
+    full = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20)
+    sep = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20, flags=_cabi.FLAG_SECOND_ORDER | _cabi.FLAG_SEPARABLE)
+    first = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20, flags=0)
+    assert_indices(full, ref)
+    assert_indices(sep, ref)
+    assert_indices(first, ref, names=("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t"))
+    assert first.sens_2 is None
+    again = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20)
+    for name in NAMES:                                                      # fixed-order reductions: bit-reproducible
+        assert (getattr(again, name) == getattr(full, name)).all()
+
+
+def test_fused_scaled_discard_raw(ctx):
+    from varsens_b200 import _cabi
+    k, n = 6, 700
+    lb, ub = numpy.linspace(0.1, 0.3, k), numpy.linspace(0.6, 0.95, k)
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, A6, discard=9, scale=_cabi.Scale(_cabi.SCALE_LINEAR, lb, ub))
+    assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, A6, discard=9, scale=("linear", lb, ub)))
+    lo, up = numpy.linspace(0.05, 0.2, k), numpy.linspace(0.7, 1.0, k)
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, A6, scale=_cabi.Scale(_cabi.SCALE_POWER, lo, up))
+    assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, A6, scale=("power", lo, up)))
+    raw = numpy.random.RandomState(3).rand(2 * n, k)
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, A6, raw=raw)
+    assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, A6, raw=raw))
+
+
+def test_fused_shards_equal_whole(ctx):
+    k, n = 20, 3000
+    p = perm_of(n)
+    whole = ctx.fused_partials(k, n, p, cport.OBJ_GFUNCTION, A20)
+    acc = numpy.zeros_like(whole)
+    for lo, hi in ((0, 1000), (1000, 1001), (1001, 2990), (2990, 3000), (3000, 3000)):
+        acc += ctx.fused_partials(k, n, p, cport.OBJ_GFUNCTION, A20, i_begin=lo, i_end=hi)
+    numpy.testing.assert_allclose(acc, whole, rtol=1e-13, atol=1e-12)
+    assert_indices(ctx.finalize(k, 1, n, acc), cport.run(k, n, cport.OBJ_GFUNCTION, A20))
+
+
+def test_fused_ishigami(ctx):
+    from varsens_b200 import _cabi
+    pi = math.pi
+    n = 1 << 14
+    sc = _cabi.Scale(_cabi.SCALE_LINEAR, numpy.full(3, -pi), numpy.full(3, pi))
+    res = ctx.run_fused(3, n, perm_of(n), cport.OBJ_ISHIGAMI, [7.0, 0.1], scale=sc)
+    assert_indices(res, cport.run(3, n, cport.OBJ_ISHIGAMI, [7.0, 0.1], scale=("linear", [-pi] * 3, [pi] * 3)))
+
+
+def test_eval_values_and_rk4(ctx):
+    from varsens_b200 import _cabi
+    k, n = 20, 64
+    ref = numpy.array([1.0] * 10 + [0.5] * 10)
+    sc = _cabi.Scale(_cabi.SCALE_POWER, ref / 10.0, ref * 10.0)
+    got = ctx.eval_values(k, n, perm_of(n), cport.OBJ_RK4_CHAIN, [0.01, 300], scale=sc)
+    want = cport.values(k, n, cport.OBJ_RK4_CHAIN, [0.01, 300], scale=("power", ref / 10.0, ref * 10.0))
+    numpy.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-14)          # tolerance: FMA contraction over 300 steps
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_RK4_CHAIN, [0.01, 300], scale=sc)
+    assert_indices(res, cport.run(k, n, cport.OBJ_RK4_CHAIN, [0.01, 300], scale=("power", ref / 10.0, ref * 10.0)),
+                   names=("E_2", "var_y"))
+    for kk in (2, 6, 22, 40):                                                # templated and run-time link counts
+        r = numpy.linspace(0.5, 2.0, kk)
+        got = ctx.eval_values(kk, 16, perm_of(16), cport.OBJ_RK4_CHAIN, [0.02, 50], scale=_cabi.Scale(_cabi.SCALE_LINEAR, r * 0.5, r * 2))
+        want = cport.values(kk, 16, cport.OBJ_RK4_CHAIN, [0.02, 50], scale=("linear", r * 0.5, r * 2))
+        numpy.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-15)
+    got = ctx.eval_values(6, 100, perm_of(100), cport.OBJ_GFUNCTION, A6, i_begin=10, i_end=77)
+    want = cport.values(6, 100, cport.OBJ_GFUNCTION, A6, i0=10, i1=77)
+    numpy.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------
+# host mirror: the reference's API
+# ------------------------------------------------------------------------------------------------
+def test_api_readme_example(vb, refgold):
+    """README.md:28-40 with the reference's own Python objective (one call per row)."""
+    def gi_function(xi, ai): return (numpy.abs(4.0 * xi - 2.0) + ai) / (1.0 + ai)
+    def g_function(x, a): return numpy.prod([gi_function(xi, a[i]) for i, xi in enumerate(x)])
+    def g_scaling(x): return x
+    def g_objective(x): return g_function(x, [0, 0.5, 3, 9, 99, 99])
+    v = vb.Varsens(g_objective, g_scaling, 6, 1024, verbose=False)
+    for name in NAMES:
+        got = numpy.asarray(getattr(v, name))
+        close(got, refgold["c1_" + name].reshape(got.shape))
+    assert v.sens.shape == (6, 1) and v.sens_2.shape == (6, 1, 6, 1) and v.E_2.shape == (1,)
+    assert (v.objective.flat() == refgold["c1_obj_flat"]).all()              # same rows -> same Python results
+    assert (v.sample.flat()[refgold["c1_flat_rows_probe"]] == refgold["c1_flat_probe"]).all()
+
+
+def test_api_three_routes_agree(vb, refgold):
+    import torch
+    s = vb.Sample(6, 1024, lambda x: x, verbose=False)
+    v_functor = vb.Varsens(vb.GFunction(A6), sample=s, verbose=False)
+
+    @vb.vectorized
+    def g_torch(X):
+        a = torch.tensor(A6, dtype=torch.float64, device=X.device)
+        return torch.prod((torch.abs(4.0 * X - 2.0) + a) / (1.0 + a), dim=1)
+
+    v_torch = vb.Varsens(g_torch, sample=s, verbose=False)
+    o = vb.Objective(6, 1024, objective_vals=refgold["c1_obj_flat"], verbose=False)
+    v_vals = vb.Varsens(o, verbose=False)
+    for v in (v_functor, v_torch, v_vals):
+        for name in NAMES:
+            got = numpy.asarray(getattr(v, name))
+            close(got, refgold["c1_" + name].reshape(got.shape))
+    # lazily materialised attributes have the reference's shapes
+    assert s.M_1.shape == (1024, 6) and s.N_j.shape == (6, 1024, 6) and s.N_nj.shape == (6, 1024, 6)
+    fo = vb.Objective(6, 1024, s, vb.GFunction(A6), verbose=False)
+    assert fo.fM_1.shape == (1024, 1) and fo.fN_j.shape == (6, 1024, 1)
+    numpy.testing.assert_allclose(fo.flat(), refgold["c1_obj_flat"], rtol=1e-13)
+
+
+def test_api_two_outputs_and_scalings(vb, refgold):
+    s = vb.Sample(6, 256, lambda x: x, verbose=False)
+    v = vb.Varsens(lambda x: [ob.g_function_row(x, A6), ob.g_function_row(x, A6[::-1])], sample=s, verbose=False)
+    for name in NAMES:
+        got = numpy.asarray(getattr(v, name))
+        assert got.shape == refgold["two_" + name].shape
+        close(got, refgold["two_" + name])
+    lb, ub = refgold["lin_lb"], refgold["lin_ub"]
+    s = vb.Sample(5, 13, lambda x: vb.scale.linear(x, lb, ub), 7, False)
+    assert (s.flat() == refgold["lin_flat_k5_n13_discard7"]).all()
+    s = vb.Sample(3, 11, lambda x: vb.scale.percentage(x, numpy.array([1.0, 10.0, 1000.0]), 33.0), verbose=False)
+    assert (s.flat() == refgold["pct_flat_k3_n11"]).all()
+    s = vb.Sample(5, 13, lambda x: numpy.sqrt(x) * 2.0 - 0.25, verbose=False)            # untraceable -> host callable
+    o = osalt.Sample(5, 13, lambda x: numpy.sqrt(x) * 2.0 - 0.25, verbose=False)
+    assert (s.flat() == o.flat()).all()
+    raw = refgold["raw_in"].copy()
+    s = vb.Sample(4, 10, lambda x: vb.scale.linear(x, -1.0, 2.0), verbose=False, raw=raw)
+    assert (s.flat() == refgold["raw_flat_k4_n10"]).all() and (raw == refgold["raw_in"]).all()
+    assert (s.generate_N_j(s.M_1, s.M_2) == s.N_j).all() and (s.generate_N_j(s.M_2, s.M_1) == s.N_nj).all()
+
+
+def test_api_reference_unit_tests(vb):
+    """varsens/tests/test_sample.py and test_objective.py restated against the GPU-backed classes."""
+    x = vb.Sample(11, 13, lambda x: x, 0, False)
+    assert x.k == 11 and x.n == 13 and x.M_1.shape == (13, 11) and x.M_2.shape == (13, 11)
+    assert x.N_j.shape == (11, 13, 11) and x.N_nj.shape == (11, 13, 11)
+    x = vb.Sample(7, 11, lambda x: x, 0, False)
+    for m in (x.M_1, x.M_2, x.N_j, x.N_nj):
+        assert (m >= 0).all() and (m <= 1).all()
+    x = vb.Sample(3, 5, lambda x: x, 0, False)
+    for i in range(3):
+        assert (x.M_1[:, i] == x.N_j[i][:, i]).all() and (x.M_2[:, i] == x.N_nj[i][:, i]).all()
+        for j in range(3):
+            if j != i:
+                assert (x.M_1[:, j] == x.N_nj[i][:, j]).all() and (x.M_2[:, j] == x.N_j[i][:, j]).all()
+    x = vb.Sample(17, 1024, lambda x: x, 0, False)
+    assert abs(numpy.sum(x.M_1) / x.n / x.k - 0.5) < 5e-3 and abs(numpy.sum(x.N_nj) / x.n / x.k / x.k - 0.5) < 5e-3
+    s = vb.Sample(5, 13, lambda x: x, 0, False)
+    assert s.flat().shape == (13 * 12, 5)
+    assert numpy.sum(s.M_1[0]) == numpy.sum(s.flat()[0]) and numpy.sum(s.N_nj[4][-1]) == numpy.sum(s.flat()[-1])
+    s = vb.Sample(8, 23, lambda x: x, 0, False)
+    o = vb.Objective(8, 23, s, lambda x: 1.0 - x, verbose=False)
+    assert o.fM_1.shape == (23, 8) and o.fN_j.shape == (8, 23, 8)
+    assert abs(numpy.sum(1.0 - o.fM_1 - s.M_1)) < 1e-12 and abs(numpy.sum(1.0 - o.fN_nj - s.N_nj)) < 1e-9
+    with pytest.raises(ValueError):
+        vb.Varsens(lambda x: 0.0)
+    with pytest.raises(Exception, match="requires that a 'scaling'"):
+        vb.Sample(3, 5)
+    with pytest.raises(Exception, match="Raw sample dimensions"):
+        vb.Sample(3, 5, raw=numpy.zeros((9, 3)))
+
+
+def test_api_export_load_round_trip(vb, tmp_path, refgold, capsys):
+    """varsens/tests/test_import_export.py:69-96: export batches -> evaluate -> load == direct run; plus NaN trimming."""
+    k, n = 6, 1024
+    s = vb.Sample(k, n, lambda x: x, verbose=False)
+    v = vb.Varsens(lambda x: ob.g_function_row(x, A6), sample=s, verbose=False)
+    s.export(str(tmp_path), "batch", ".csv", 2000)
+    nfiles = int(math.ceil(2 * n * (1 + k) / 2000.0))
+    for i in range(nfiles):
+        rows = numpy.loadtxt(str(tmp_path / ("batch_%d.csv" % (i + 1))))
+        numpy.savetxt(str(tmp_path / ("obj_%d.csv" % (i + 1))), ob.g_function_rows(rows, A6))
+    o = vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="obj", postfix=".csv", nFiles=nfiles)
+    v2 = vb.Varsens(o, sample=s, verbose=False)
+    for name in NAMES:
+        numpy.testing.assert_allclose(getattr(v2, name), getattr(v, name), rtol=0, atol=5e-8)    # 7 places, as the reference test
+    s2 = vb.Sample(k, n, verbose=False, indir=str(tmp_path), prefix="batch", postfix=".csv", nFiles=nfiles)
+    assert (s2.M_2 == s.M_2).all() and (s2.N_nj == s.N_nj).all()
+    o3 = vb.Objective(6, 256, objective_vals=refgold["nan_obj_in"], verbose=False)
+    assert tuple(o3.fM_1.shape) == tuple(refgold["nan_fM_1_shape"])
+    v3 = vb.Varsens(o3, verbose=False)
+    for name in ("E_2", "var_y", "sens", "sens_t", "sens_2"):
+        got = numpy.asarray(getattr(v3, name))
+        close(got, refgold["nan_" + name].reshape(got.shape))
+    assert "WARNING: 2 of 3584 objectives were NaN" in capsys.readouterr().out
+
+
+# ------------------------------------------------------------------------------------------------
+# larger sizes: oracle at n = 2^18, analytic truths and invariances at BASELINE's full size
+# ------------------------------------------------------------------------------------------------
+def test_fused_k20_n2p18_against_c_oracle(ctx):
+    n = 1 << 18
+    res = ctx.run_fused(20, n, perm_of(n), cport.OBJ_GFUNCTION, A20)
+    assert_indices(res, cport.run(20, n, cport.OBJ_GFUNCTION, A20))
+
+
+def test_fused_full_size_c3_properties(ctx):
+    """BASELINE config 3 (k=20, n=2^24): closed-form truths (test_g_function.py:20-50) to 3e-3, the generic and
+    separable kernels agree to 1e-10, and a 2-shard split reproduces the single launch."""
+    from varsens_b200 import _cabi
+    k, n = 20, 1 << 24
+    p = perm_of(n)
+    res = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20)
+    var = float(res.var_y[0])
+    assert abs(var - ob.g_var(A20)) < 3e-3 and abs(float(res.E_2[0]) - 1.0) < 3e-3
+    truth = ob.g_truth(A20)
+    for i in range(k):
+        assert abs(res.sens[i, 0] * var - truth[i]) < 3e-3
+        assert abs(res.sens_t[i, 0] * var - ob.g_truth_t(A20, i)) < 3e-3
+    for i, j in ((0, 1), (0, 2), (1, 3), (4, 19)):
+        assert abs(res.sens_2[i, 0, j, 0] * var - ob.g_truth_2(A20, i, j)) < 3e-3
+        assert abs(res.sens_2n[i, 0, j, 0] * var - ob.g_truth_vnc(A20, [i, j])) < 3e-3
+    assert numpy.allclose(res.sens_2[:, 0, :, 0], res.sens_2[:, 0, :, 0].T, rtol=0, atol=1e-15)
+    sep = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20, flags=_cabi.FLAG_SECOND_ORDER | _cabi.FLAG_SEPARABLE)
+    for name in NAMES:
+        close(getattr(sep, name), getattr(res, name))
+    import torch
+    pd = torch.from_numpy(p.astype(numpy.int32)).cuda()
+    acc = ctx.fused_partials(k, n, pd, cport.OBJ_GFUNCTION, A20, i_begin=0, i_end=n // 2 + 7)
+    acc = acc + ctx.fused_partials(k, n, pd, cport.OBJ_GFUNCTION, A20, i_begin=n // 2 + 7, i_end=n)
+    two = ctx.finalize(k, 1, n, acc)
+    for name in NAMES:
+        close(getattr(two, name), getattr(res, name))

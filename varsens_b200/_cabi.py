@@ -1,0 +1,323 @@
+"""ctypes binding of libvarsens_b200.so (include/varsens_b200.h).
+
+The library is the only compute path: if it is missing or no CUDA device is present the calls
+raise -- there is no CPU fallback (BASELINE.json north_star).
+"""
+import ctypes
+import os
+import threading
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvarsens_b200.so")
+
+VS_OK = 0
+MEM_HOST, MEM_DEVICE = 0, 1
+SCALE_IDENTITY, SCALE_LINEAR, SCALE_POWER = 0, 1, 2
+OBJ_GFUNCTION, OBJ_ISHIGAMI, OBJ_RK4_CHAIN = 0, 1, 2
+FLAG_SECOND_ORDER, FLAG_SEPARABLE = 1, 2
+
+# every symbol include/varsens_b200.h declares (tests/test_cabi_symbols.py checks the header against this)
+SYMBOLS = (
+    "vs_abi_version", "vs_last_error", "vs_ctx_create", "vs_ctx_destroy", "vs_ctx_set_stream",
+    "vs_ctx_synchronize", "vs_ctx_launch_count", "vs_halton_bases", "vs_halton_terms", "vs_partials_len",
+    "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
+    "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
+)
+
+
+class VarsensError(RuntimeError):
+    pass
+
+
+class vs_scale(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p)]
+
+
+class vs_result(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_void_p) for name in
+                ("E_2", "var_y", "U_j", "U_nj", "sens", "sens_t", "sens_2", "sens_2n")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the shared library (once).  Raises VarsensError if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise VarsensError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C varsens_b200/csrc).  varsens_b200 has no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        u64, i32, vp, sz = ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+        P = ctypes.POINTER
+        L.vs_abi_version.restype = i32
+        L.vs_last_error.restype = ctypes.c_char_p
+        L.vs_ctx_create.argtypes = [i32, P(vp)]
+        L.vs_ctx_destroy.argtypes = [vp]
+        L.vs_ctx_set_stream.argtypes = [vp, vp]
+        L.vs_ctx_synchronize.argtypes = [vp]
+        L.vs_ctx_launch_count.argtypes = [vp]
+        L.vs_ctx_launch_count.restype = u64
+        L.vs_halton_bases.argtypes = [i32, vp]
+        L.vs_halton_terms.argtypes = [i32, u64, vp, vp, vp, u64, P(u64)]
+        L.vs_partials_len.argtypes = [i32, i32]
+        L.vs_partials_len.restype = sz
+        L.vs_halton.argtypes = [vp, i32, u64, u64, P(vs_scale), vp, i32]
+        L.vs_sobol.argtypes = [vp, i32, u64, u64, vp, i32, P(vs_scale), vp, i32]
+        L.vs_sample_flat.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), u64, u64, vp, i32]
+        L.vs_eval_values.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, vp, i32]
+        L.vs_partials_from_values.argtypes = [vp, i32, i32, u64, vp, i32, vp, i32, vp, i32]
+        L.vs_finalize.argtypes = [vp, i32, i32, u64, vp, i32, i32, P(vs_result)]
+        L.vs_indices_from_values.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
+        L.vs_fused_partials.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32,
+                                        vp, i32]
+        L.vs_run_fused.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, i32, P(vs_result)]
+        L.vs_measure_fp64_peak.argtypes = [vp, P(ctypes.c_double)]
+        L.vs_last_kernel_ms.argtypes = [vp, P(ctypes.c_float)]
+        for name in SYMBOLS:
+            fn = getattr(L, name)
+            if fn.restype is ctypes.c_int and name not in ("vs_abi_version",):
+                pass
+        _lib = L
+        return _lib
+
+
+def check(status):
+    if status != VS_OK:
+        raise VarsensError("libvarsens_b200: status %d: %s" % (status, lib().vs_last_error().decode()))
+
+
+def _is_torch_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def buf(x, dtype=None):
+    """(pointer, mem flag, keepalive) for a numpy array or torch tensor (None -> NULL)."""
+    if x is None:
+        return None, MEM_HOST, None
+    if _is_torch_tensor(x):
+        if not x.is_contiguous():
+            raise VarsensError("tensor must be contiguous")
+        if dtype is not None:
+            import torch
+            want = {numpy.float64: torch.float64, numpy.uint32: torch.int32}[dtype]
+            if x.dtype not in (want, getattr(torch, "uint32", want)):
+                raise VarsensError("tensor dtype %s, expected %s" % (x.dtype, want))
+        return ctypes.c_void_p(x.data_ptr()), (MEM_DEVICE if x.is_cuda else MEM_HOST), x
+    a = numpy.ascontiguousarray(x, dtype=dtype)
+    return a.ctypes.data_as(ctypes.c_void_p), MEM_HOST, a
+
+
+class Scale(object):
+    """Host descriptor lowered to vs_scale (identity / linear / power)."""
+
+    def __init__(self, kind=SCALE_IDENTITY, lower=None, upper=None):
+        self.kind, self.lower, self.upper = kind, lower, upper
+
+    def c_struct(self, k):
+        if self.kind == SCALE_IDENTITY:
+            return None, None
+        lo = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(self.lower, dtype=numpy.float64), (k,)))
+        up = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(self.upper, dtype=numpy.float64), (k,)))
+        s = vs_scale(self.kind, lo.ctypes.data_as(ctypes.c_void_p), up.ctypes.data_as(ctypes.c_void_p))
+        return ctypes.byref(s), (s, lo, up)
+
+    def apply_numpy(self, p):
+        """Same arithmetic on the host (used only to validate a traced scaling callable)."""
+        if self.kind == SCALE_LINEAR:
+            return p * (numpy.asarray(self.upper) - numpy.asarray(self.lower)) + numpy.asarray(self.lower)
+        if self.kind == SCALE_POWER:
+            return numpy.asarray(self.lower) * ((numpy.asarray(self.upper) / numpy.asarray(self.lower)) ** p)
+        return p
+
+
+IDENTITY = Scale()
+
+
+class Result(object):
+    """Host arrays shaped like the reference's attributes (varsens/saltelli.py:577-622)."""
+
+    def __init__(self, k, l, second_order=True):
+        self.k, self.l = k, l
+        self.E_2 = numpy.zeros(l)
+        self.var_y = numpy.zeros(l)
+        self.U_j = numpy.zeros((k, l))
+        self.U_nj = numpy.zeros((k, l))
+        self.sens = numpy.zeros((k, l))
+        self.sens_t = numpy.zeros((k, l))
+        self.sens_2 = numpy.zeros((k, l, k, l)) if second_order else None
+        self.sens_2n = numpy.zeros((k, l, k, l)) if second_order else None
+
+    def c_struct(self):
+        def p(a):
+            return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        return vs_result(p(self.E_2), p(self.var_y), p(self.U_j), p(self.U_nj), p(self.sens), p(self.sens_t),
+                         p(self.sens_2), p(self.sens_2n))
+
+
+class Context(object):
+    """One vs_ctx per (process, device)."""
+
+    _cache = {}
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib().vs_ctx_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        if device not in cls._cache:
+            cls._cache[device] = Context(device)
+        return cls._cache[device]
+
+    def close(self):
+        if self._h:
+            lib().vs_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(lib().vs_ctx_synchronize(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().vs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def launch_count(self):
+        return int(lib().vs_ctx_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        check(lib().vs_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def measure_fp64_peak(self):
+        t = ctypes.c_double()
+        check(lib().vs_measure_fp64_peak(self._h, ctypes.byref(t)))
+        return float(t.value)
+
+    # ---- generators -----------------------------------------------------------------------
+    def halton(self, k, first_index, count, scale=IDENTITY, out=None):
+        out = numpy.empty((int(count), int(k))) if out is None else out
+        sp, keep = scale.c_struct(k)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_halton(self._h, int(k), int(first_index), int(count), sp, op, om))
+        return out
+
+    def sobol(self, k, first_point, count, dirnums, quantize6=False, scale=IDENTITY, out=None):
+        out = numpy.empty((int(count), int(k))) if out is None else out
+        d = numpy.ascontiguousarray(dirnums, dtype=numpy.uint32)
+        if d.shape != (k, 32):
+            raise VarsensError("dirnums must have shape (k, 32)")
+        sp, keep = scale.c_struct(k)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_sobol(self._h, int(k), int(first_point), int(count), d.ctypes.data_as(ctypes.c_void_p),
+                             int(bool(quantize6)), sp, op, om))
+        return out
+
+    def sample_flat(self, k, n, perm, discard=0, scale=IDENTITY, raw=None, row_begin=0, row_end=None, out=None):
+        total = 2 * n * (1 + k)
+        row_end = total if row_end is None else row_end
+        out = numpy.empty((int(row_end - row_begin), int(k))) if out is None else out
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_sample_flat(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(row_begin),
+                                   int(row_end), op, om))
+        return out
+
+    # ---- objective values / estimators --------------------------------------------------------
+    def eval_values(self, k, n, perm, objective, params, discard=0, scale=IDENTITY, raw=None, i_begin=0, i_end=None,
+                    out=None):
+        i_end = n if i_end is None else i_end
+        out = numpy.empty((2 + 2 * k, int(i_end - i_begin))) if out is None else out
+        par = numpy.ascontiguousarray(params, dtype=numpy.float64)
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_eval_values(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                                   par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end), op, om))
+        return out
+
+    def partials_from_values(self, k, l, rows, fvals, shift=None, flags=FLAG_SECOND_ORDER, out=None):
+        plen = int(lib().vs_partials_len(int(k), int(l)))
+        out = numpy.empty(plen) if out is None else out
+        fp, fm, fk = buf(fvals, numpy.float64)
+        sh = None if shift is None else numpy.ascontiguousarray(shift, dtype=numpy.float64)
+        shp = None if sh is None else sh.ctypes.data_as(ctypes.c_void_p)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_partials_from_values(self._h, int(k), int(l), int(rows), fp, fm, shp, int(flags), op, om))
+        return out
+
+    def finalize(self, k, l, n, partials, flags=FLAG_SECOND_ORDER):
+        res = Result(k, l, bool(flags & FLAG_SECOND_ORDER))
+        cs = res.c_struct()
+        pp, pm, pk = buf(partials, numpy.float64)
+        check(lib().vs_finalize(self._h, int(k), int(l), int(n), pp, pm, int(flags), ctypes.byref(cs)))
+        return res
+
+    def indices_from_values(self, k, l, n, rows, fvals, flags=FLAG_SECOND_ORDER):
+        res = Result(k, l, bool(flags & FLAG_SECOND_ORDER))
+        cs = res.c_struct()
+        fp, fm, fk = buf(fvals, numpy.float64)
+        check(lib().vs_indices_from_values(self._h, int(k), int(l), int(n), int(rows), fp, fm, int(flags),
+                                           ctypes.byref(cs)))
+        return res
+
+    # ---- fused ------------------------------------------------------------------------------------
+    def fused_partials(self, k, n, perm, objective, params, discard=0, scale=IDENTITY, raw=None, i_begin=0, i_end=None,
+                       flags=FLAG_SECOND_ORDER, out=None):
+        i_end = n if i_end is None else i_end
+        plen = int(lib().vs_partials_len(int(k), 1))
+        out = numpy.empty(plen) if out is None else out
+        par = numpy.ascontiguousarray(params, dtype=numpy.float64)
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        op, om, _ = buf(out, numpy.float64)
+        check(lib().vs_fused_partials(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                                      par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end),
+                                      int(flags), op, om))
+        return out
+
+    def run_fused(self, k, n, perm, objective, params, discard=0, scale=IDENTITY, raw=None, flags=FLAG_SECOND_ORDER):
+        res = Result(k, 1, bool(flags & FLAG_SECOND_ORDER))
+        cs = res.c_struct()
+        par = numpy.ascontiguousarray(params, dtype=numpy.float64)
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        check(lib().vs_run_fused(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                                 par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(flags), ctypes.byref(cs)))
+        return res
+
+
+def halton_terms(k, max_index):
+    """Host-only: the library's term table (bases, ndigits, offsets, terms)."""
+    L = lib()
+    bases = numpy.zeros(k, dtype=numpy.uint32)
+    check(L.vs_halton_bases(int(k), bases.ctypes.data_as(ctypes.c_void_p)))
+    cnt = ctypes.c_uint64()
+    nd = numpy.zeros(k, dtype=numpy.uint32)
+    off = numpy.zeros(k, dtype=numpy.uint32)
+    check(L.vs_halton_terms(int(k), int(max_index), nd.ctypes.data_as(ctypes.c_void_p),
+                            off.ctypes.data_as(ctypes.c_void_p), None, 0, ctypes.byref(cnt)))
+    terms = numpy.zeros(int(cnt.value))
+    check(L.vs_halton_terms(int(k), int(max_index), nd.ctypes.data_as(ctypes.c_void_p),
+                            off.ctypes.data_as(ctypes.c_void_p), terms.ctypes.data_as(ctypes.c_void_p),
+                            int(cnt.value), ctypes.byref(cnt)))
+    return bases, nd, off, terms

@@ -1,0 +1,274 @@
+// extern "C" entry points (see include/varsens_b200.h for the contract of each).
+#include <cstring>
+#include <vector>
+
+#include "vs_internal.cuh"
+
+using namespace vs;
+
+namespace {
+
+// Output staging: run into `dev` (caller's device buffer or scratch), then copy to the host buffer.
+struct OutStage {
+    vs_ctx *c;
+    void *user;
+    int mem;
+    size_t bytes;
+    void *dev = nullptr;
+    int begin(DevBuf &scratch) {
+        if (mem == VS_MEM_DEVICE) {
+            dev = user;
+            return VS_OK;
+        }
+        VS_REQUIRE(mem == VS_MEM_HOST, VS_ERR_ARG, "bad memory flag %d", mem);
+        VS_TRY(ensure(c, scratch, bytes));
+        dev = scratch.p;
+        return VS_OK;
+    }
+    int end() {
+        if (mem == VS_MEM_HOST) {
+            VS_CUDA(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+            VS_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return VS_OK;
+    }
+};
+
+int check_common(vs_ctx *c, int k) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    VS_REQUIRE(k >= 1 && k <= 4096, VS_ERR_ARG, "k=%d out of range [1,4096]", k);
+    VS_CUDA(cudaSetDevice(c->device));
+    return VS_OK;
+}
+
+int copy_result(vs_ctx *c, int k, int l, int flags, const double *res_dev, vs_result *r) {
+    size_t len = result_len(k, l);
+    std::vector<double> h(len);
+    VS_CUDA(cudaMemcpyAsync(h.data(), res_dev, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    size_t kl = (size_t)k * l;
+    const double *p = h.data();
+    auto take = [&](double *dst, size_t cnt) {
+        if (dst) memcpy(dst, p, cnt * sizeof(double));
+        p += cnt;
+    };
+    take(r->E_2, l);
+    take(r->var_y, l);
+    take(r->U_j, kl);
+    take(r->U_nj, kl);
+    take(r->sens, kl);
+    take(r->sens_t, kl);
+    if (flags & VS_FLAG_SECOND_ORDER) {
+        take(r->sens_2, kl * kl);
+        take(r->sens_2n, kl * kl);
+    }
+    return VS_OK;
+}
+
+}  // namespace
+
+extern "C" int vs_halton(vs_ctx *c, int k, uint64_t first_index, uint64_t count, const vs_scale *scale, double *out,
+                         int out_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(first_index >= 1, VS_ERR_ARG, "Halton indices are 1-based");
+    if (count == 0) return VS_OK;
+    VS_REQUIRE(out, VS_ERR_ARG, "out is NULL");
+    HaltonDev h;
+    VS_TRY(get_halton(c, k, first_index + count - 1, &h));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    OutStage o{c, out, out_mem, count * (uint64_t)k * sizeof(double)};
+    VS_TRY(o.begin(c->io_buf));
+    VS_TRY(launch_halton(c, k, first_index, count, h, s, (double *)o.dev));
+    return o.end();
+}
+
+extern "C" int vs_sobol(vs_ctx *c, int k, uint64_t first_point, uint64_t count, const uint32_t *dirnums, int quantize6,
+                        const vs_scale *scale, double *out, int out_mem) {
+    VS_TRY(check_common(c, k));
+    if (count == 0) return VS_OK;
+    VS_REQUIRE(out && dirnums, VS_ERR_ARG, "NULL argument");
+    VS_REQUIRE(first_point + count - 1 < (1ull << 32), VS_ERR_RANGE, "Sobol point number does not fit 32 bits");
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    VS_TRY(ensure(c, c->dir_buf, (size_t)k * 32 * sizeof(uint32_t)));
+    VS_CUDA(cudaMemcpyAsync(c->dir_buf.p, dirnums, (size_t)k * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    OutStage o{c, out, out_mem, count * (uint64_t)k * sizeof(double)};
+    VS_TRY(o.begin(c->io_buf));
+    VS_TRY(launch_sobol(c, k, first_point, count, (const uint32_t *)c->dir_buf.p, quantize6, s, (double *)o.dev));
+    VS_TRY(o.end());
+    if (out_mem == VS_MEM_DEVICE) VS_CUDA(cudaStreamSynchronize(c->stream));   // dirnums is caller memory
+    return VS_OK;
+}
+
+extern "C" int vs_sample_flat(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                              const double *raw, int raw_mem, const vs_scale *scale, uint64_t row_begin, uint64_t row_end,
+                              double *out, int out_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 1, VS_ERR_ARG, "n must be >= 1");
+    uint64_t total = 2 * n * (1 + (uint64_t)k);
+    VS_REQUIRE(row_begin <= row_end && row_end <= total, VS_ERR_ARG, "row window [%llu,%llu) outside [0,%llu)",
+               (unsigned long long)row_begin, (unsigned long long)row_end, (unsigned long long)total);
+    if (row_begin == row_end) return VS_OK;
+    VS_REQUIRE(out, VS_ERR_ARG, "out is NULL");
+    SourceDev src;
+    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, 0, n, raw, raw_mem, &src));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    OutStage o{c, out, out_mem, (row_end - row_begin) * (uint64_t)k * sizeof(double)};
+    VS_TRY(o.begin(c->io_buf));
+    VS_TRY(launch_sample_flat(c, k, src, s, row_begin, row_end, (double *)o.dev));
+    VS_TRY(o.end());
+    if (out_mem == VS_MEM_DEVICE && (perm_mem == VS_MEM_HOST || (raw && raw_mem == VS_MEM_HOST)))
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_eval_values(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                              const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                              int n_params, uint64_t i_begin, uint64_t i_end, double *fvals, int fvals_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 1 && i_begin <= i_end && i_end <= n, VS_ERR_ARG, "bad row range");
+    if (i_begin == i_end) return VS_OK;
+    VS_REQUIRE(fvals, VS_ERR_ARG, "fvals is NULL");
+    SourceDev src;
+    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, i_end - i_begin, raw, raw_mem, &src));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    ObjectiveDev od;
+    VS_TRY(get_objective(c, k, objective, params, n_params, &od));
+    OutStage o{c, fvals, fvals_mem, (i_end - i_begin) * (uint64_t)(2 + 2 * k) * sizeof(double)};
+    VS_TRY(o.begin(c->io_buf));
+    VS_TRY(launch_eval_values(c, k, src, s, od, i_begin, i_end, (double *)o.dev));
+    VS_TRY(o.end());
+    if (fvals_mem == VS_MEM_DEVICE) VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, int fvals_mem,
+                                       const double *shift, int flags, double *partials, int partials_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(l >= 1 && l <= 64, VS_ERR_ARG, "l=%d out of range [1,64]", l);
+    VS_REQUIRE(partials && (fvals || rows == 0), VS_ERR_ARG, "NULL argument");
+    size_t plen = vs_partials_len(k, l);
+    OutStage o{c, partials, partials_mem, plen * sizeof(double)};
+    VS_TRY(o.begin(c->part_buf));
+    if (rows == 0) {
+        VS_CUDA(cudaMemsetAsync(o.dev, 0, plen * sizeof(double), c->stream));
+        return o.end();
+    }
+    const void *fdev = nullptr;
+    VS_TRY(stage_in(c, c->io_buf, fvals, fvals_mem, rows * (uint64_t)(2 + 2 * k) * l * sizeof(double), &fdev));
+    const double *shift_dev = nullptr;
+    if (shift) {
+        VS_TRY(ensure(c, c->misc_buf, 64 * sizeof(double)));
+        VS_CUDA(cudaMemcpyAsync(c->misc_buf.p, shift, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        shift_dev = (const double *)c->misc_buf.p;
+    }
+    VS_TRY(launch_partials_from_values(c, k, l, rows, (const double *)fdev, shift_dev, flags, (double *)o.dev));
+    VS_TRY(o.end());
+    if (partials_mem == VS_MEM_DEVICE) VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int partials_mem, int flags,
+                           vs_result *result) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && partials && result, VS_ERR_ARG, "bad arguments");
+    const void *pdev = nullptr;
+    VS_TRY(stage_in(c, c->part_buf, partials, partials_mem, vs_partials_len(k, l) * sizeof(double), &pdev));
+    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
+    VS_TRY(launch_finalize(c, k, l, n, (const double *)pdev, flags, (double *)c->res_buf.p));
+    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+}
+
+extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *fvals, int fvals_mem,
+                                      int flags, vs_result *result) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && fvals && result, VS_ERR_ARG, "bad arguments");
+    const void *fdev = nullptr;
+    VS_TRY(stage_in(c, c->io_buf, fvals, fvals_mem, rows * (uint64_t)(2 + 2 * k) * l * sizeof(double), &fdev));
+    // common shift = first row of fM_1 (any value works; this one is cheap and data-scaled)
+    VS_TRY(ensure(c, c->misc_buf, 64 * sizeof(double)));
+    VS_CUDA(cudaMemcpyAsync(c->misc_buf.p, fdev, l * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    VS_TRY(ensure(c, c->part_buf, vs_partials_len(k, l) * sizeof(double)));
+    VS_TRY(launch_partials_from_values(c, k, l, rows, (const double *)fdev, (const double *)c->misc_buf.p, flags,
+                                       (double *)c->part_buf.p));
+    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
+    VS_TRY(launch_finalize(c, k, l, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
+    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+}
+
+static int fused_partials_dev(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                              const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                              int n_params, uint64_t i_begin, uint64_t i_end, int flags, double *partials_dev) {
+    SourceDev src;
+    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, i_end - i_begin, raw, raw_mem, &src));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    ObjectiveDev od;
+    VS_TRY(get_objective(c, k, objective, params, n_params, &od));
+    if (fused_supported(k, objective, flags))
+        return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev);
+    // Two-phase path on the GPU: values to HBM scratch, then the Gram reduction.
+    VS_REQUIRE(!(flags & VS_FLAG_SEPARABLE), VS_ERR_UNSUPPORTED, "VS_FLAG_SEPARABLE needs a fused kernel (objective %d, k=%d)",
+               objective, k);
+    uint64_t rows = i_end - i_begin;
+    VS_TRY(ensure(c, c->io_buf, rows * (uint64_t)(2 + 2 * k) * sizeof(double)));
+    VS_TRY(launch_eval_values(c, k, src, s, od, i_begin, i_end, (double *)c->io_buf.p));
+    // common shift f(M_1[0]) must not depend on the shard: evaluate base row 0 separately
+    VS_TRY(ensure(c, c->misc_buf, (size_t)(64 + 2 + 2 * k) * sizeof(double)));
+    if (i_begin == 0) {
+        VS_CUDA(cudaMemcpyAsync(c->misc_buf.p, c->io_buf.p, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        SourceDev src0 = src;
+        if (perm_mem == VS_MEM_HOST) {   // row 0's permutation entry is outside the staged slice
+            VS_TRY(ensure(c, c->dir_buf, 256));
+            VS_CUDA(cudaMemcpyAsync(c->dir_buf.p, perm, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+            src0.perm = (const uint32_t *)c->dir_buf.p;
+        }
+        double *tmp = (double *)c->misc_buf.p + 64;
+        VS_TRY(launch_eval_values(c, k, src0, s, od, 0, 1, tmp));
+        VS_CUDA(cudaMemcpyAsync(c->misc_buf.p, tmp, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return launch_partials_from_values(c, k, 1, rows, (const double *)c->io_buf.p, (const double *)c->misc_buf.p, flags,
+                                       partials_dev);
+}
+
+extern "C" int vs_fused_partials(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                                 const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                                 int n_params, uint64_t i_begin, uint64_t i_end, int flags, double *partials, int partials_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 2 && i_begin <= i_end && i_end <= n && partials, VS_ERR_ARG, "bad arguments");
+    size_t plen = vs_partials_len(k, 1);
+    OutStage o{c, partials, partials_mem, plen * sizeof(double)};
+    VS_TRY(o.begin(c->part_buf));
+    if (i_begin == i_end) {
+        VS_CUDA(cudaMemsetAsync(o.dev, 0, plen * sizeof(double), c->stream));
+        return o.end();
+    }
+    VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, i_begin,
+                              i_end, flags, (double *)o.dev));
+    VS_TRY(o.end());
+    if (partials_mem == VS_MEM_DEVICE) VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" int vs_run_fused(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                            const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                            int n_params, int flags, vs_result *result) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 2 && result, VS_ERR_ARG, "bad arguments");
+    VS_TRY(ensure(c, c->part_buf, vs_partials_len(k, 1) * sizeof(double)));
+    VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, 0, n, flags,
+                              (double *)c->part_buf.p));
+    VS_TRY(ensure(c, c->res_buf, result_len(k, 1) * sizeof(double)));
+    VS_TRY(launch_finalize(c, k, 1, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
+    return copy_result(c, k, 1, flags, (const double *)c->res_buf.p, result);
+}
+
+extern "C" int vs_measure_fp64_peak(vs_ctx *c, double *tflops) {
+    VS_REQUIRE(c && tflops, VS_ERR_ARG, "NULL argument");
+    VS_CUDA(cudaSetDevice(c->device));
+    return launch_fp64_peak(c, tflops);
+}

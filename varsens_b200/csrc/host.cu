@@ -1,0 +1,346 @@
+// Context, error reporting, scratch management and host-built tables.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "vs_internal.cuh"
+
+namespace vs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return VS_ERR_CUDA;
+}
+
+int ensure(vs_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return VS_OK;
+    if (b.p) {
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        VS_CUDA(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        (void)cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return VS_ERR_NOMEM;
+    }
+    b.cap = want;
+    return VS_OK;
+}
+
+int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, const void **dev) {
+    if (mem == VS_MEM_DEVICE) {
+        *dev = p;
+        return VS_OK;
+    }
+    VS_REQUIRE(mem == VS_MEM_HOST, VS_ERR_ARG, "bad memory flag %d", mem);
+    VS_TRY(ensure(c, scratch, bytes));
+    VS_CUDA(cudaMemcpyAsync(scratch.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = scratch.p;
+    return VS_OK;
+}
+
+void time_begin(vs_ctx *c) {
+    cudaEventRecord(c->ev0, c->stream);
+}
+void time_end(vs_ctx *c) {
+    cudaEventRecord(c->ev1, c->stream);
+    c->timed = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halton bases and term table
+// ---------------------------------------------------------------------------------------------
+static void first_primes(int k, std::vector<uint32_t> &p) {
+    p.clear();
+    for (uint32_t v = 2; (int)p.size() < k; ++v) {
+        bool prime = true;
+        for (size_t i = 0; i < p.size() && (uint64_t)p[i] * p[i] <= v; ++i)
+            if (v % p[i] == 0) { prime = false; break; }
+        if (prime) p.push_back(v);
+    }
+}
+
+static void digit_counts(const std::vector<uint32_t> &bases, uint64_t max_index, std::vector<uint32_t> &nd) {
+    nd.resize(bases.size());
+    for (size_t d = 0; d < bases.size(); ++d) {
+        uint32_t c = 0;
+        for (uint64_t m = max_index; m > 0; m /= bases[d]) ++c;
+        nd[d] = c ? c : 1;
+    }
+}
+
+// The one place that fixes the generator's fp64 arithmetic: term = (double)digit / (double)b^(j+1),
+// with b^(j+1) accumulated as ghalton does (bp *= b; exact for every index range we accept).
+static void build_terms(const std::vector<uint32_t> &bases, const std::vector<uint32_t> &nd, std::vector<uint32_t> &off,
+                        std::vector<double> &terms) {
+    off.resize(bases.size());
+    terms.clear();
+    for (size_t d = 0; d < bases.size(); ++d) {
+        off[d] = (uint32_t)terms.size();
+        volatile double bp = (double)bases[d];
+        for (uint32_t j = 0; j < nd[d]; ++j) {
+            for (uint32_t digit = 0; digit < bases[d]; ++digit) {
+                volatile double q = (double)digit / bp;
+                terms.push_back((double)q);
+            }
+            bp = bp * (double)bases[d];
+        }
+    }
+}
+
+int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
+    VS_REQUIRE(max_index < (1ull << 32), VS_ERR_RANGE, "Halton index %llu does not fit 32 bits",
+               (unsigned long long)max_index);
+    std::vector<uint32_t> bases, nd;
+    first_primes(k, bases);
+    digit_counts(bases, max_index, nd);
+    HaltonCache &hc = c->halton;
+    bool hit = hc.blob && hc.k == k && hc.ndigits.size() == nd.size();
+    if (hit)
+        for (size_t d = 0; d < nd.size(); ++d)
+            if (hc.ndigits[d] < nd[d]) { hit = false; break; }
+    if (!hit) {
+        std::vector<uint32_t> off;
+        std::vector<double> terms;
+        build_terms(bases, nd, off, terms);
+        std::vector<uint64_t> magic(k);
+        for (int d = 0; d < k; ++d) magic[d] = (~0ull) / bases[d] + 1ull;   // floor((2^64-1)/b)+1 == floor(2^64/b)+1 for b not a power of 2; b=2 unused
+        size_t nb_terms = terms.size() * sizeof(double), nb_magic = (size_t)k * 8, nb_u32 = (size_t)k * 4;
+        size_t total = nb_terms + nb_magic + 2 * nb_u32 + 64;
+        if (hc.blob) {
+            VS_CUDA(cudaStreamSynchronize(c->stream));
+            VS_CUDA(cudaFree(hc.blob));
+            hc.blob = nullptr;
+        }
+        VS_CUDA(cudaMalloc(&hc.blob, total));
+        char *p = (char *)hc.blob;
+        VS_CUDA(cudaMemcpy(p, terms.data(), nb_terms, cudaMemcpyHostToDevice));
+        hc.dev.terms = (const double *)p;
+        p += nb_terms;
+        VS_CUDA(cudaMemcpy(p, magic.data(), nb_magic, cudaMemcpyHostToDevice));
+        hc.dev.magic = (const uint64_t *)p;
+        p += nb_magic;
+        VS_CUDA(cudaMemcpy(p, bases.data(), nb_u32, cudaMemcpyHostToDevice));
+        hc.dev.base = (const uint32_t *)p;
+        p += nb_u32;
+        VS_CUDA(cudaMemcpy(p, off.data(), nb_u32, cudaMemcpyHostToDevice));
+        hc.dev.off = (const uint32_t *)p;
+        hc.dev.total_terms = (uint32_t)terms.size();
+        hc.k = k;
+        hc.ndigits = nd;
+    }
+    *out = hc.dev;
+    return VS_OK;
+}
+
+int get_scale(vs_ctx *c, int k, const vs_scale *s, ScaleDev *out) {
+    out->kind = VS_SCALE_IDENTITY;
+    out->lb = out->wr = nullptr;
+    if (!s || s->kind == VS_SCALE_IDENTITY) return VS_OK;
+    VS_REQUIRE(s->kind == VS_SCALE_LINEAR || s->kind == VS_SCALE_POWER, VS_ERR_ARG, "unknown scale kind %d", s->kind);
+    VS_REQUIRE(s->lower && s->upper, VS_ERR_ARG, "scale bounds are NULL");
+    std::vector<double> h(2 * (size_t)k);
+    for (int d = 0; d < k; ++d) {
+        volatile double lo = s->lower[d], up = s->upper[d];
+        volatile double wr = (s->kind == VS_SCALE_LINEAR) ? (up - lo) : (up / lo);   // scale.py:33 / :62
+        h[d] = lo;
+        h[k + d] = wr;
+    }
+    VS_TRY(ensure(c, c->scale_buf, h.size() * sizeof(double)));
+    VS_CUDA(cudaMemcpyAsync(c->scale_buf.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VS_CUDA(cudaStreamSynchronize(c->stream));   // h is a stack-lifetime vector
+    out->kind = s->kind;
+    out->lb = (const double *)c->scale_buf.p;
+    out->wr = out->lb + k;
+    return VS_OK;
+}
+
+int get_objective(vs_ctx *c, int k, int objective, const double *params, int n_params, ObjectiveDev *out) {
+    std::vector<double> h;
+    switch (objective) {
+    case VS_OBJ_GFUNCTION:
+        VS_REQUIRE(params && n_params == k, VS_ERR_ARG, "g-function needs k=%d parameters a_c, got %d", k, n_params);
+        h.resize(3 * (size_t)k);
+        for (int d = 0; d < k; ++d) {
+            VS_REQUIRE(params[d] > -1.0, VS_ERR_ARG, "g-function needs a_c > -1");
+            h[d] = params[d];
+            h[k + d] = 1.0 / (1.0 + params[d]);
+            h[2 * k + d] = params[d] / (1.0 + params[d]);
+        }
+        break;
+    case VS_OBJ_ISHIGAMI:
+        VS_REQUIRE(k >= 3, VS_ERR_ARG, "Ishigami needs k >= 3");
+        VS_REQUIRE(params && n_params == 2, VS_ERR_ARG, "Ishigami needs parameters {A, B}");
+        h.assign(params, params + 2);
+        break;
+    case VS_OBJ_RK4_CHAIN:
+        VS_REQUIRE(k >= 2 && k % 2 == 0 && k / 2 <= 64, VS_ERR_ARG, "RK4 chain needs even k with k/2 <= 64 links");
+        VS_REQUIRE(params && n_params == 2 && params[1] >= 0, VS_ERR_ARG, "RK4 chain needs parameters {dt, nsteps}");
+        h.assign(params, params + 2);
+        break;
+    default:
+        set_error("unknown objective id %d", objective);
+        return VS_ERR_ARG;
+    }
+    VS_TRY(ensure(c, c->obj_buf, h.size() * sizeof(double)));
+    VS_CUDA(cudaMemcpyAsync(c->obj_buf.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    out->id = objective;
+    out->params = (const double *)c->obj_buf.p;
+    out->n_params = (int)h.size();
+    return VS_OK;
+}
+
+int make_source(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem, uint64_t perm_begin,
+                uint64_t perm_count, const double *raw, int raw_mem, SourceDev *out) {
+    memset(out, 0, sizeof(*out));
+    VS_REQUIRE(perm, VS_ERR_ARG, "perm is NULL");
+    out->n = n;
+    out->start = 20ull * (uint64_t)k + discard + 1ull;          // saltelli.py:83: 20k + discard points skipped
+    if (raw) {
+        const void *d = nullptr;
+        VS_TRY(stage_in(c, c->raw_buf, raw, raw_mem, 2 * n * (uint64_t)k * sizeof(double), &d));
+        out->raw = (const double *)d;
+    } else {
+        uint64_t last = out->start + 2 * n - 1;
+        VS_TRY(get_halton(c, k, last, &out->h));
+    }
+    // perm is indexed by the absolute base row i; stage only the slice a shard needs.
+    const void *d = nullptr;
+    if (perm_mem == VS_MEM_DEVICE) {
+        out->perm = perm;
+    } else {
+        VS_TRY(stage_in(c, c->perm_buf, perm + perm_begin, VS_MEM_HOST, perm_count * sizeof(uint32_t), &d));
+        out->perm = (const uint32_t *)d - perm_begin;
+    }
+    return VS_OK;
+}
+
+}  // namespace vs
+
+// ---------------------------------------------------------------------------------------------
+// extern "C": library / context / host helpers
+// ---------------------------------------------------------------------------------------------
+using namespace vs;
+
+extern "C" int vs_abi_version(void) { return VS_ABI_VERSION; }
+
+extern "C" const char *vs_last_error(void) { return g_err; }
+
+extern "C" int vs_ctx_create(int device, vs_ctx **out) {
+    VS_REQUIRE(out, VS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s); varsens_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return VS_ERR_CUDA;
+    }
+    VS_REQUIRE(device >= 0 && device < count, VS_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    VS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VS_CUDA(cudaGetDeviceProperties(&prop, device));
+    VS_REQUIRE(prop.major >= 10, VS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+               device, prop.major, prop.minor);
+    vs_ctx *c = new vs_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    VS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    VS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    VS_CUDA(cudaEventCreate(&c->ev0));
+    VS_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_destroy(vs_ctx *c) {
+    if (!c) return VS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
+                      &c->part_buf,  &c->block_buf, &c->res_buf, &c->dir_buf, &c->misc_buf};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->halton.blob) cudaFree(c->halton.blob);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_set_stream(vs_ctx *c, void *stream) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    VS_CUDA(cudaSetDevice(c->device));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_synchronize(vs_ctx *c) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    VS_CUDA(cudaSetDevice(c->device));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
+extern "C" uint64_t vs_ctx_launch_count(const vs_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int vs_last_kernel_ms(vs_ctx *c, float *ms) {
+    VS_REQUIRE(c && ms, VS_ERR_ARG, "NULL argument");
+    VS_REQUIRE(c->timed, VS_ERR_ARG, "no timed kernel has run on this ctx");
+    VS_CUDA(cudaSetDevice(c->device));
+    VS_CUDA(cudaEventSynchronize(c->ev1));
+    VS_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return VS_OK;
+}
+
+extern "C" int vs_halton_bases(int k, uint32_t *bases) {
+    VS_REQUIRE(k > 0 && bases, VS_ERR_ARG, "bad arguments");
+    std::vector<uint32_t> b;
+    first_primes(k, b);
+    memcpy(bases, b.data(), sizeof(uint32_t) * k);
+    return VS_OK;
+}
+
+extern "C" int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offsets, double *terms,
+                               uint64_t capacity, uint64_t *count) {
+    VS_REQUIRE(k > 0 && count, VS_ERR_ARG, "bad arguments");
+    std::vector<uint32_t> bases, nd, off;
+    std::vector<double> t;
+    first_primes(k, bases);
+    digit_counts(bases, max_index, nd);
+    build_terms(bases, nd, off, t);
+    *count = t.size();
+    if (ndigits) memcpy(ndigits, nd.data(), sizeof(uint32_t) * k);
+    if (offsets) memcpy(offsets, off.data(), sizeof(uint32_t) * k);
+    if (terms) {
+        VS_REQUIRE(capacity >= t.size(), VS_ERR_ARG, "terms capacity %llu < %zu", (unsigned long long)capacity, t.size());
+        memcpy(terms, t.data(), sizeof(double) * t.size());
+    }
+    return VS_OK;
+}
+
+extern "C" size_t vs_partials_len(int k, int l) {
+    size_t m = (size_t)(2 + 2 * k) * (size_t)l;
+    return 4 * (size_t)l + m * (m + 1) / 2;
+}

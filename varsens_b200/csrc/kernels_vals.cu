@@ -1,0 +1,391 @@
+// Objective evaluation to HBM (two-phase path), Gram/partial-sum reduction of given values, finalisation.
+#include "device.cuh"
+
+namespace vs {
+
+// ---------------------------------------------------------------------------------------------
+// Two-phase path, phase 1: objective values of base rows, sample rows generated on the fly.
+// One thread per (base row, point chunk).  The row's A_i / B_i live in shared memory, transposed
+// ([coordinate][thread]) so every access is conflict-free; a point of the design is a *view*
+// (base row, one substituted column) -- the 2+2k sample rows are never materialised.
+// Replaces varsens/saltelli.py:308-353.  Used for heavy functors (RK4: one trajectory per thread)
+// and for any k the fused kernel does not cover.
+// ---------------------------------------------------------------------------------------------
+struct SmemPoint {
+    const double *base, *other;
+    int j, stride;
+    __device__ __forceinline__ double operator[](int c) const { return (c == j ? other : base)[c * stride]; }
+};
+
+template <class F>
+__global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end,
+                                   double *__restrict__ fvals) {
+    extern __shared__ double smem[];
+    const int nthr = blockDim.x;
+    double *A = smem + threadIdx.x;                       // A[c*nthr]
+    double *B = smem + (size_t)k * nthr + threadIdx.x;
+    const uint64_t rows = i_end - i_begin;
+    const uint64_t r = (uint64_t)blockIdx.x * nthr + threadIdx.x;
+    if (r >= rows) return;
+    const uint64_t i = i_begin + r;
+    const uint64_t pi = src.perm[i];
+    for (int c = 0; c < k; ++c) {
+        A[c * nthr] = apply_scale(s, c, source_a(src, k, i, c));
+        B[c * nthr] = apply_scale(s, c, source_b(src, k, pi, c));
+    }
+    const int npts = 2 + 2 * k;
+    int p0 = blockIdx.y * pts_per_chunk, p1 = p0 + pts_per_chunk;
+    if (p1 > npts) p1 = npts;
+    for (int p = p0; p < p1; ++p) {
+        SmemPoint x;
+        x.stride = nthr;
+        if (p == 0) { x.base = A; x.other = A; x.j = -1; }
+        else if (p == 1) { x.base = B; x.other = B; x.j = -1; }
+        else if (p < 2 + k) { x.base = B; x.other = A; x.j = p - 2; }          // N_j[j]  : M_2 with col j from M_1
+        else { x.base = A; x.other = B; x.j = p - 2 - k; }                      // N_nj[j] : M_1 with col j from M_2
+        fvals[(uint64_t)p * rows + r] = f(x, k);
+    }
+}
+
+template <class F>
+static int launch_eval_t(vs_ctx *c, int k, bool heavy, const SourceDev &src, const ScaleDev &s, const F &f, uint64_t i_begin,
+                         uint64_t i_end, double *fvals) {
+    uint64_t rows = i_end - i_begin;
+    if (rows == 0) return VS_OK;
+    int nthr = 128;
+    while (nthr > 32 && 2 * (size_t)k * nthr * sizeof(double) > 96 * 1024) nthr >>= 1;
+    size_t smem = 2 * (size_t)k * nthr * sizeof(double);
+    VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "k=%d does not fit shared memory", k);
+    if (smem > 48 * 1024) VS_CUDA(cudaFuncSetAttribute(eval_values_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int npts = 2 + 2 * k;
+    int ppc = heavy ? 1 : npts;
+    dim3 grid((unsigned)((rows + nthr - 1) / nthr), (unsigned)((npts + ppc - 1) / ppc));
+    time_begin(c);
+    eval_values_kernel<F><<<grid, nthr, smem, c->stream>>>(k, ppc, src, s, f, i_begin, i_end, fvals);
+    time_end(c);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+template <int S>
+static int launch_rk4(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, double dt, int nsteps, uint64_t i_begin,
+                      uint64_t i_end, double *fvals) {
+    RK4Chain<S> f{dt, nsteps};
+    return launch_eval_t(c, k, true, src, s, f, i_begin, i_end, fvals);
+}
+
+int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
+                       uint64_t i_end, double *fvals) {
+    switch (o.id) {
+    case VS_OBJ_GFUNCTION: {
+        GFunction f{o.params + k, o.params + 2 * k};
+        return launch_eval_t(c, k, false, src, s, f, i_begin, i_end, fvals);
+    }
+    case VS_OBJ_ISHIGAMI: {
+        double h[2];
+        VS_CUDA(cudaMemcpyAsync(h, o.params, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        Ishigami f{h[0], h[1]};
+        return launch_eval_t(c, k, false, src, s, f, i_begin, i_end, fvals);
+    }
+    case VS_OBJ_RK4_CHAIN: {
+        double h[2];
+        VS_CUDA(cudaMemcpyAsync(h, o.params, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        double dt = h[0];
+        int ns = (int)h[1];
+        switch (k / 2) {
+#define VS_RK4_CASE(S) case S: return launch_rk4<S>(c, k, src, s, dt, ns, i_begin, i_end, fvals);
+            VS_RK4_CASE(1) VS_RK4_CASE(2) VS_RK4_CASE(3) VS_RK4_CASE(4) VS_RK4_CASE(5) VS_RK4_CASE(6)
+            VS_RK4_CASE(7) VS_RK4_CASE(8) VS_RK4_CASE(9) VS_RK4_CASE(10) VS_RK4_CASE(12) VS_RK4_CASE(16)
+#undef VS_RK4_CASE
+        default: {
+            RK4ChainDyn f{dt, ns};
+            return launch_eval_t(c, k, true, src, s, f, i_begin, i_end, fvals);
+        }
+        }
+    }
+    }
+    set_error("unknown objective id %d", o.id);
+    return VS_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Estimator reductions on given values: symmetric Gram G = sum_i v_i v_i^T of the per-row vector
+// v_i (m = (2+2k) l entries) + shifted sums for var_y.  Everything the estimators of
+// varsens/saltelli.py:577-622 need is an entry of G (only 3 distinct k x k Grams).
+//
+// CTA: stages R rows of v in shared memory (coalesced loads of the t-major value layout), then
+// every thread accumulates one T x T register tile of the upper triangle over a subset of the
+// staged rows (2T shared loads per T^2 DFMA).  Row groups and CTAs are combined in a fixed order
+// -> bit-reproducible results.
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(256) gram_kernel(GramGeom g, uint64_t rows, const double *__restrict__ fvals,
+                                                   const double *__restrict__ shift, double *__restrict__ blockpart) {
+    extern __shared__ double smem[];
+    double *Y = smem;  // [R][mp]
+    const int tid = threadIdx.x;
+    const int grp = tid / g.LG, tl = tid - grp * g.LG;
+    const int tile = blockIdx.y * g.LG + tl;
+    const bool active = (grp < g.RG) && (tile < g.ntiles);
+    int tr = 0, tc = 0;
+    if (active) tile_coords(tile, g.nt, tr, tc);
+    double acc[T][T];
+#pragma unroll
+    for (int x = 0; x < T; ++x)
+#pragma unroll
+        for (int y = 0; y < T; ++y) acc[x][y] = 0.0;
+    // shifted sums: thread e < 2l of pass 0 owns (t = e / l in {0,1}, o = e % l)
+    const bool sum_thread = (blockIdx.y == 0) && (tid < 2 * g.l);
+    const double my_shift = (sum_thread && shift) ? shift[tid % g.l] : 0.0;
+    double sS = 0.0, sQ = 0.0;
+
+    const uint64_t nchunks = (rows + g.R - 1) / g.R;
+    for (uint64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const uint64_t r0 = ch * g.R;
+        const int valid = (int)((rows - r0 < (uint64_t)g.R) ? rows - r0 : g.R);
+        // stage: global element (t, r, o) at fvals[(t*rows + r0 + r)*l + o] -> Y[r][t*l + o]
+        const int per_t = g.R * g.l;
+        const int nT = g.m / g.l;
+        for (int e = tid; e < nT * per_t; e += blockDim.x) {
+            int t = e / per_t, rem = e - t * per_t;
+            int r = rem / g.l, o = rem - r * g.l;
+            double v = (r < valid) ? fvals[((uint64_t)t * rows + r0 + r) * g.l + o] : 0.0;
+            Y[r * g.mp + t * g.l + o] = v;
+        }
+        for (int e = tid; e < g.R * (g.mp - g.m); e += blockDim.x) {   // zero the column padding
+            int r = e / (g.mp - g.m), cidx = g.m + e % (g.mp - g.m);
+            Y[r * g.mp + cidx] = 0.0;
+        }
+        __syncthreads();
+        if (active) {
+            for (int r = grp; r < g.R; r += g.RG) {
+                const double *row = Y + r * g.mp;
+                double a[T], b[T];
+#pragma unroll
+                for (int x = 0; x < T; ++x) { a[x] = row[tr * T + x]; b[x] = row[tc * T + x]; }
+#pragma unroll
+                for (int x = 0; x < T; ++x)
+#pragma unroll
+                    for (int y = 0; y < T; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+            }
+        }
+        if (sum_thread) {
+            for (int r = 0; r < valid; ++r) {
+                double d = Y[r * g.mp + tid] - my_shift;
+                sS += d;
+                sQ = fma(d, d, sQ);
+            }
+        }
+        __syncthreads();
+    }
+    // combine row groups in fixed order through shared memory: red[grp][tl][T*T]
+    double *red = smem;
+    if (grp < g.RG && tl < g.LG) {
+#pragma unroll
+        for (int x = 0; x < T; ++x)
+#pragma unroll
+            for (int y = 0; y < T; ++y) red[((size_t)grp * g.LG + tl) * (T * T) + x * T + y] = acc[x][y];
+    }
+    __syncthreads();
+    const size_t per_block = (size_t)g.passes * g.LG * (T * T) + 4 * (size_t)g.l;
+    double *bp = blockpart + (size_t)blockIdx.x * per_block;
+    for (int e = tid; e < g.LG * T * T; e += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < g.RG; ++q) s += red[(size_t)q * g.LG * (T * T) + e];
+        bp[(size_t)blockIdx.y * g.LG * (T * T) + e] = s;
+    }
+    if (sum_thread) {
+        double *ss = bp + (size_t)g.passes * g.LG * (T * T);
+        ss[tid] = sS;                 // S_A[l], S_B[l]
+        ss[2 * g.l + tid] = sQ;       // Q_A[l], Q_B[l]
+    }
+}
+
+// Sum CTA partials in CTA order and scatter tile entries into the packed upper triangle.
+template <int T>
+__global__ void __launch_bounds__(256) gram_scatter_kernel(GramGeom g, int nblocks, const double *__restrict__ blockpart,
+                                                           double *__restrict__ partials) {
+    const size_t tile_elems = (size_t)g.passes * g.LG * (T * T);
+    const size_t per_block = tile_elems + 4 * (size_t)g.l;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = gid; e < per_block; e += nthreads) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + e];
+        if (e >= tile_elems) {
+            partials[e - tile_elems] = s;
+            continue;
+        }
+        int slot = (int)(e / (T * T)), within = (int)(e % (T * T));
+        int pass = slot / g.LG, tl = slot % g.LG;
+        int tile = pass * g.LG + tl;
+        if (tile >= g.ntiles) continue;
+        int tr, tc;
+        tile_coords(tile, g.nt, tr, tc);
+        int p = tr * T + within / T, q = tc * T + within % T;
+        if (p >= g.m || q >= g.m || p > q) continue;
+        size_t off = 4 * (size_t)g.l + (size_t)p * g.m - (size_t)p * (p - 1) / 2 + (size_t)(q - p);
+        partials[off] = s;
+    }
+}
+
+int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
+
+static GramGeom make_geom(int k, int l, int flags, int T) {
+    GramGeom g{};
+    g.l = l;
+    g.m = (2 + 2 * k) * l;
+    g.T = T;
+    g.nt = (g.m + T - 1) / T;
+    g.mp = g.nt * T;
+    if (g.mp % 2 == 0) g.mp += 1;
+    g.tr_max = (flags & VS_FLAG_SECOND_ORDER) ? g.nt : (2 * l + T - 1) / T;
+    if (g.tr_max > g.nt) g.tr_max = g.nt;
+    g.ntiles = 0;
+    for (int tr = 0; tr < g.tr_max; ++tr) g.ntiles += g.nt - tr;
+    int lg = ((g.ntiles + 31) / 32) * 32;
+    if (lg > 256) lg = 256;
+    g.LG = lg;
+    g.RG = 256 / lg;
+    g.passes = (g.ntiles + lg - 1) / lg;
+    int R = (int)((64 * 1024) / ((size_t)g.mp * sizeof(double)));
+    if (R > 64) R = 64;
+    if (R < g.RG) R = g.RG;
+    R = (R / g.RG) * g.RG;
+    g.R = R;
+    return g;
+}
+
+static double geom_cost(const GramGeom &g) {
+    // DFMA issue slots per staged row, per CTA (lower is better)
+    return (double)g.passes * g.LG * g.T * g.T / (double)(g.RG);
+}
+
+template <int T>
+static int launch_gram_t(vs_ctx *c, const GramGeom &g, uint64_t rows, const double *fvals, const double *shift_dev,
+                         double *partials, int plen) {
+    size_t smem_stage = (size_t)g.R * g.mp * sizeof(double);
+    size_t smem_red = (size_t)g.RG * g.LG * T * T * sizeof(double);
+    size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
+    VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "Gram tile needs %zu bytes of shared memory", smem);
+    VS_CUDA(cudaFuncSetAttribute(gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t nchunks = (rows + g.R - 1) / g.R;
+    int gx = (int)(nchunks < (uint64_t)(2 * c->sm_count) ? nchunks : (uint64_t)(2 * c->sm_count));
+    if (gx < 1) gx = 1;
+    size_t per_block = (size_t)g.passes * g.LG * (T * T) + 4 * (size_t)g.l;
+    VS_TRY(ensure(c, c->block_buf, (size_t)gx * per_block * sizeof(double)));
+    time_begin(c);
+    gram_kernel<T><<<dim3(gx, g.passes), 256, smem, c->stream>>>(g, rows, fvals, shift_dev, (double *)c->block_buf.p);
+    time_end(c);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return launch_gram_scatter(c, g, gx, (const double *)c->block_buf.p, partials, plen);
+}
+
+int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen) {
+    VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
+    size_t per_block = (size_t)g.passes * g.LG * (g.T * g.T) + 4 * (size_t)g.l;
+    int rb = (int)((per_block + 255) / 256);
+    switch (g.T) {
+    case 4: gram_scatter_kernel<4><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
+    case 6: gram_scatter_kernel<6><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
+    case 8: gram_scatter_kernel<8><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
+    default: set_error("unsupported Gram tile %d", g.T); return VS_ERR_ARG;
+    }
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+int launch_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev,
+                                int flags, double *partials) {
+    int plen = (int)vs_partials_len(k, l);
+    GramGeom best = make_geom(k, l, flags, 4);
+    for (int T : {6, 8}) {
+        GramGeom g = make_geom(k, l, flags, T);
+        if (geom_cost(g) < geom_cost(best)) best = g;
+    }
+    switch (best.T) {
+    case 4: return launch_gram_t<4>(c, best, rows, fvals, shift_dev, partials, plen);
+    case 6: return launch_gram_t<6>(c, best, rows, fvals, shift_dev, partials, plen);
+    default: return launch_gram_t<8>(c, best, rows, fvals, shift_dev, partials, plen);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalisation: the estimators of varsens/saltelli.py:577-622 on the sufficient statistics, same
+// operation order (E_2 over n; U and Grams over n-1; mixed normalisation is the reference's).
+// Result buffer: E_2[l] var_y[l] U_j[kl] U_nj[kl] sens[kl] sens_t[kl] sens_2[(kl)^2] sens_2n[(kl)^2]
+// ---------------------------------------------------------------------------------------------
+size_t result_len(int k, int l) {
+    size_t kl = (size_t)k * l;
+    return 2 * (size_t)l + 4 * kl + 2 * kl * kl;
+}
+
+__device__ __forceinline__ double gram_at(const double *G, int m, int p, int q) {
+    if (p > q) { int t = p; p = q; q = t; }
+    return G[(size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)];
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, const double *__restrict__ P, int second_order,
+                                                       double *__restrict__ res) {
+    const int m = (2 + 2 * k) * l;
+    const double *G = P + 4 * l;
+    const int kl = k * l;
+    double *E2 = res, *var = res + l, *Uj = res + 2 * l, *Unj = Uj + kl, *sens = Unj + kl, *senst = sens + kl;
+    double *s2 = senst + kl, *s2n = s2 + (size_t)kl * kl;
+    __shared__ double sE2[64], sVar[64];
+    for (int o = threadIdx.x; o < l; o += blockDim.x) {
+        double e2 = gram_at(G, m, 0 * l + o, 1 * l + o) / n;                                  // :577
+        double tot = P[o] + P[l + o];
+        double v = (P[2 * l + o] + P[3 * l + o] - tot * tot / (2.0 * n)) / (2.0 * n - 1.0);    // :583
+        E2[o] = e2;
+        var[o] = v;
+        if (o < 64) { sE2[o] = e2; sVar[o] = v; }
+    }
+    __syncthreads();
+    auto e2_of = [&](int o) { return o < 64 ? sE2[o] : E2[o]; };
+    auto var_of = [&](int o) { return o < 64 ? sVar[o] : var[o]; };
+    for (int e = threadIdx.x; e < kl; e += blockDim.x) {
+        int j = e / l, o = e - j * l;
+        int iA = o, iB = l + o, iJ = (2 + j) * l + o, iN = (2 + k + j) * l + o;
+        double uj = gram_at(G, m, iA, iJ) / (n - 1.0);                                        // :591-593
+        uj += gram_at(G, m, iB, iN) / (n - 1.0);
+        uj /= 2.0;
+        double unj = gram_at(G, m, iA, iN) / (n - 1.0);                                       // :594-596
+        unj += gram_at(G, m, iB, iJ) / (n - 1.0);
+        unj /= 2.0;
+        Uj[e] = uj;
+        Unj[e] = unj;
+        sens[e] = (uj - e2_of(o)) / var_of(o);                                                // :608
+        senst[e] = 1.0 - ((unj - e2_of(o)) / var_of(o));                                      // :609
+    }
+    if (!second_order) return;
+    for (size_t e = threadIdx.x; e < (size_t)kl * kl; e += blockDim.x) {
+        int ia = (int)(e / kl), jb = (int)(e % kl);
+        int i = ia / l, a = ia - i * l, j = jb / l, b = jb - j * l;
+        int Ji = (2 + i) * l + a, Ni = (2 + k + i) * l + a, Jj = (2 + j) * l + b, Nj = (2 + k + j) * l + b;
+        double v2 = gram_at(G, m, Ni, Jj) + gram_at(G, m, Ji, Nj);                            // :612-613
+        v2 /= 2.0 * (n - 1.0);
+        v2 -= e2_of(b);
+        v2 /= var_of(b);
+        double v2n = gram_at(G, m, Ni, Nj) + gram_at(G, m, Ji, Jj);                           // :618-619
+        v2n /= 2.0 * (n - 1.0);
+        v2n -= e2_of(b);
+        v2n /= var_of(b);
+        s2[e] = v2;
+        s2n[e] = v2n;
+    }
+}
+
+int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int flags, double *res_dev) {
+    finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0, res_dev);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+}  // namespace vs

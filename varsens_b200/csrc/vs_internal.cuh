@@ -1,0 +1,153 @@
+// Internal declarations shared by the translation units of libvarsens_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/varsens_b200.h"
+
+namespace vs {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define VS_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::vs::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define VS_TRY(call)                \
+    do {                            \
+        int s__ = (call);           \
+        if (s__ != VS_OK) return s__; \
+    } while (0)
+
+#define VS_REQUIRE(cond, code, ...)   \
+    do {                              \
+        if (!(cond)) {                \
+            ::vs::set_error(__VA_ARGS__); \
+            return (code);            \
+        }                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-side descriptors (plain structs passed by value to kernels)
+// ---------------------------------------------------------------------------------------------
+// Halton term table: terms[off[d] + j*base[d] + digit] = digit / base[d]^(j+1) (host-built, fp64
+// division; see vs_halton_terms).  magic[d] = floor(2^64 / base[d]) + 1 gives an exact quotient
+// of any 32-bit index by one 64-bit mul-high.
+struct HaltonDev {
+    const double *terms;
+    const uint32_t *base;
+    const uint64_t *magic;
+    const uint32_t *off;
+    uint32_t total_terms;
+};
+
+// scale.py:33 / :62 lowered: linear  -> p * w + lb   (w = ub - lb rounded on the host, as numpy does)
+//                            power   -> lb * pow(r, p) (r = ub / lb rounded on the host)
+struct ScaleDev {
+    int kind;
+    const double *lb;
+    const double *wr;
+};
+
+// Where the unscaled points of the base design come from.
+struct SourceDev {
+    HaltonDev h;            // Halton (raw == nullptr)
+    const double *raw;      // or an unscaled (2n,k) matrix
+    const uint32_t *perm;   // row permutation of M_2
+    uint64_t n;
+    uint64_t start;         // Halton index of base row 0 of M_1: 20k + discard + 1
+};
+
+// Geometry of a tiled upper-triangular Gram accumulation (kernels_vals.cu, kernels_fused.cu).
+// Tile `id` (row-major over tr < tr_max, tc >= tr) covers G[tr*T .. tr*T+T)[tc*T .. tc*T+T).
+struct GramGeom {
+    int m, l, T, nt, mp;        // mp = padded length of a staged row (odd -> conflict-free transposed stores)
+    int ntiles, tr_max;
+    int LG, RG;                 // lanes per tile group (multiple of 32), row groups per CTA
+    int R;                      // rows staged per iteration
+    int passes;
+};
+
+struct ObjectiveDev {
+    int id;
+    const double *params;   // device copy of the host params (plus derived values, see functors.cuh)
+    int n_params;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct HaltonCache {
+    int k = 0;
+    std::vector<uint32_t> ndigits;
+    HaltonDev dev{};
+    void *blob = nullptr;
+};
+
+}  // namespace vs
+
+struct vs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // stream the kernels run on
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    vs::HaltonCache halton;
+    // scratch
+    vs::DevBuf scale_buf, obj_buf, perm_buf, raw_buf, io_buf, part_buf, block_buf, res_buf, dir_buf, misc_buf;
+};
+
+namespace vs {
+
+int ensure(vs_ctx *c, DevBuf &b, size_t bytes);
+int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out);
+int get_scale(vs_ctx *c, int k, const vs_scale *s, ScaleDev *out);
+int get_objective(vs_ctx *c, int k, int objective, const double *params, int n_params, ObjectiveDev *out);
+// Returns a device pointer for an input buffer (staging a host buffer through `scratch`).
+int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, const void **dev);
+int make_source(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                uint64_t perm_begin, uint64_t perm_count, const double *raw, int raw_mem, SourceDev *out);
+void time_begin(vs_ctx *c);
+void time_end(vs_ctx *c);
+
+// kernels_gen.cu
+int launch_halton(vs_ctx *c, int k, uint64_t first, uint64_t count, const HaltonDev &h, const ScaleDev &s, double *out);
+int launch_sobol(vs_ctx *c, int k, uint64_t first, uint64_t count, const uint32_t *dir_dev, int quantize6,
+                 const ScaleDev &s, double *out);
+int launch_sample_flat(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, uint64_t row_begin,
+                       uint64_t row_end, double *out);
+// kernels_vals.cu
+int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o,
+                       uint64_t i_begin, uint64_t i_end, double *fvals);
+int launch_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev,
+                                int flags, double *partials);
+int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int flags, double *res_dev);
+size_t result_len(int k, int l);
+int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
+// kernels_fused.cu
+bool fused_supported(int k, int objective, int flags);
+int launch_fused(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
+                 uint64_t i_end, int flags, double *partials);
+// microbench.cu
+int launch_fp64_peak(vs_ctx *c, double *tflops);
+
+}  // namespace vs
