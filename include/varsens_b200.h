@@ -133,9 +133,11 @@ int vs_eval_values(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint3
  * rank; NULL = 0).  Replaces the reductions of varsens/saltelli.py:577-622. */
 int vs_partials_from_values(vs_ctx *ctx, int k, int l, uint64_t rows, const double *fvals, int fvals_mem,
                             const double *shift, int flags, double *partials, int partials_mem);
-/* Indices from (all-reduced) partial sums; n = the reference's divisor (saltelli.py:577,591-596). */
-int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, const double *partials, int partials_mem, int flags,
-                vs_result *result);
+/* Indices from (all-reduced) partial sums.  n = the reference's divisor (saltelli.py:577,591-596); rows =
+ * base rows that actually contributed (== n unless NaN rows were trimmed, saltelli.py:474-495: var_y is the
+ * unbiased variance of the 2*rows surviving values while E_2 and U keep dividing by n and n-1). */
+int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *partials, int partials_mem,
+                int flags, vs_result *result);
 /* vs_partials_from_values + vs_finalize over a whole design (Objective(objective_vals=...) route,
  * varsens/saltelli.py:297-298 -> :572-622).  rows may be < n after NaN trimming (:474-495). */
 int vs_indices_from_values(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *fvals,

@@ -74,7 +74,7 @@ def lib():
         L.vs_sample_flat.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), u64, u64, vp, i32]
         L.vs_eval_values.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, vp, i32]
         L.vs_partials_from_values.argtypes = [vp, i32, i32, u64, vp, i32, vp, i32, vp, i32]
-        L.vs_finalize.argtypes = [vp, i32, i32, u64, vp, i32, i32, P(vs_result)]
+        L.vs_finalize.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
         L.vs_indices_from_values.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
         L.vs_fused_partials.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32,
                                         vp, i32]
@@ -263,11 +263,12 @@ class Context(object):
         check(lib().vs_partials_from_values(self._h, int(k), int(l), int(rows), fp, fm, shp, int(flags), op, om))
         return out
 
-    def finalize(self, k, l, n, partials, flags=FLAG_SECOND_ORDER):
+    def finalize(self, k, l, n, partials, flags=FLAG_SECOND_ORDER, rows=None):
         res = Result(k, l, bool(flags & FLAG_SECOND_ORDER))
         cs = res.c_struct()
         pp, pm, pk = buf(partials, numpy.float64)
-        check(lib().vs_finalize(self._h, int(k), int(l), int(n), pp, pm, int(flags), ctypes.byref(cs)))
+        check(lib().vs_finalize(self._h, int(k), int(l), int(n), int(n if rows is None else rows), pp, pm, int(flags),
+                                ctypes.byref(cs)))
         return res
 
     def indices_from_values(self, k, l, n, rows, fvals, flags=FLAG_SECOND_ORDER):

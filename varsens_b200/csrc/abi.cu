@@ -171,14 +171,14 @@ extern "C" int vs_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, c
     return VS_OK;
 }
 
-extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int partials_mem, int flags,
-                           vs_result *result) {
+extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials, int partials_mem,
+                           int flags, vs_result *result) {
     VS_TRY(check_common(c, k));
-    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && partials && result, VS_ERR_ARG, "bad arguments");
+    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials && result, VS_ERR_ARG, "bad arguments");
     const void *pdev = nullptr;
     VS_TRY(stage_in(c, c->part_buf, partials, partials_mem, vs_partials_len(k, l) * sizeof(double), &pdev));
     VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, l, n, (const double *)pdev, flags, (double *)c->res_buf.p));
+    VS_TRY(launch_finalize(c, k, l, n, rows, (const double *)pdev, flags, (double *)c->res_buf.p));
     return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
 }
 
@@ -195,7 +195,7 @@ extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint6
     VS_TRY(launch_partials_from_values(c, k, l, rows, (const double *)fdev, (const double *)c->misc_buf.p, flags,
                                        (double *)c->part_buf.p));
     VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, l, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
+    VS_TRY(launch_finalize(c, k, l, n, rows, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
     return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
 }
 
@@ -263,7 +263,7 @@ extern "C" int vs_run_fused(vs_ctx *c, int k, uint64_t n, uint64_t discard, cons
     VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, 0, n, flags,
                               (double *)c->part_buf.p));
     VS_TRY(ensure(c, c->res_buf, result_len(k, 1) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, 1, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
+    VS_TRY(launch_finalize(c, k, 1, n, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
     return copy_result(c, k, 1, flags, (const double *)c->res_buf.p, result);
 }
 

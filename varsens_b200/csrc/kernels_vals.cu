@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(256) gram_kernel(GramGeom g, uint64_t rows, co
 }
 
 // Sum CTA partials in CTA order and scatter tile entries into the packed upper triangle.
-template <int T>
 __global__ void __launch_bounds__(256) gram_scatter_kernel(GramGeom g, int nblocks, const double *__restrict__ blockpart,
                                                            double *__restrict__ partials) {
+    const int T = g.T;
     const size_t tile_elems = (size_t)g.passes * g.LG * (T * T);
     const size_t per_block = tile_elems + 4 * (size_t)g.l;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,12 +289,7 @@ int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double 
     VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
     size_t per_block = (size_t)g.passes * g.LG * (g.T * g.T) + 4 * (size_t)g.l;
     int rb = (int)((per_block + 255) / 256);
-    switch (g.T) {
-    case 4: gram_scatter_kernel<4><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
-    case 6: gram_scatter_kernel<6><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
-    case 8: gram_scatter_kernel<8><<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials); break;
-    default: set_error("unsupported Gram tile %d", g.T); return VS_ERR_ARG;
-    }
+    gram_scatter_kernel<<<rb, 256, 0, c->stream>>>(g, nblocks, blockpart, partials);
     c->launches++;
     VS_CUDA(cudaGetLastError());
     return VS_OK;
@@ -330,7 +325,7 @@ __device__ __forceinline__ double gram_at(const double *G, int m, int p, int q) 
     return G[(size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)];
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, const double *__restrict__ P, int second_order,
+__global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
                                                        double *__restrict__ res) {
     const int m = (2 + 2 * k) * l;
     const double *G = P + 4 * l;
@@ -341,7 +336,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, c
     for (int o = threadIdx.x; o < l; o += blockDim.x) {
         double e2 = gram_at(G, m, 0 * l + o, 1 * l + o) / n;                                  // :577
         double tot = P[o] + P[l + o];
-        double v = (P[2 * l + o] + P[3 * l + o] - tot * tot / (2.0 * n)) / (2.0 * n - 1.0);    // :583
+        double v = (P[2 * l + o] + P[3 * l + o] - tot * tot / (2.0 * rows)) / (2.0 * rows - 1.0);   // :583 (ddof=1 over 2*rows values)
         E2[o] = e2;
         var[o] = v;
         if (o < 64) { sE2[o] = e2; sVar[o] = v; }
@@ -381,8 +376,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, c
     }
 }
 
-int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int flags, double *res_dev) {
-    finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0, res_dev);
+int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials, int flags, double *res_dev) {
+    finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, (double)rows, partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0, res_dev);
     c->launches++;
     VS_CUDA(cudaGetLastError());
     return VS_OK;

@@ -140,7 +140,7 @@ int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s
                        uint64_t i_begin, uint64_t i_end, double *fvals);
 int launch_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev,
                                 int flags, double *partials);
-int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, const double *partials, int flags, double *res_dev);
+int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials, int flags, double *res_dev);
 size_t result_len(int k, int l);
 int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
 // kernels_fused.cu
