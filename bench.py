@@ -140,7 +140,7 @@ class ClockSampler(object):
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
@@ -245,8 +245,8 @@ def run_gpu(args, rank, world):
     kernel_ms = []
     ms, res = timed(step_resident, args.steps, args.warmup, kernel_ms)
     launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
-    clocks = sampler.stop() if sampler else None
     ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None          # sampled over both timed regions
 
     # fused kernel alone (this rank's shard), separable shortcut for context
     sep_ms = None
@@ -274,7 +274,7 @@ def run_gpu(args, rank, world):
                 "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k))},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                     "traffic": None, "kernel": "vs::fused_kernel<20, GFunctionReg<20>, true, false>", "kernel_ms": kms,
+                     "traffic": None, "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, 2, 1> (E/S warp-specialised, DMMA Gram)", "kernel_ms": kms,
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "DFMA-chain microbenchmark run in this process (vs_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"},
         "clocks": clocks,

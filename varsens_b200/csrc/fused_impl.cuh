@@ -1,0 +1,791 @@
+// Fused pipeline: generation + scaling + assembly + objective + estimator reductions in one kernel.
+//
+// Replaces varsens/saltelli.py:82-125 (Sample), :308-353 (Objective loops) and the reductions of
+// :577-622 (Varsens.compute_varsens) for registered functors.  The sample matrices M_1, M_2, N_j,
+// N_nj (2*k*n*k*8 bytes in the reference, saltelli.py:119) never exist: a base row i is two
+// register vectors A_i, B_i and each of its 2+2k design points is a compile-time selection of
+// those registers.
+//
+// Mapping (one warp = 32 consecutive base rows per batch, persistent grid):
+//   phase 1  lane = base row.  A_i, B_i by in-order Halton digit sums (term table in shared
+//            memory), scaled; the functor is evaluated on each of the 2+2k points and the value
+//            is parked in the warp's shared tile Y[32][M].
+//   phase 2  lane = T x T register tile of the symmetric M x M Gram  G += Y^T Y  (M = 2+2k): for
+//            each of the 32 rows 2T broadcast shared loads feed T^2 DFMA.  G holds every sum the
+//            estimators need.  Shifted sums for var_y stay lane-local in phase 1.
+// Warps, then CTAs, are combined in a fixed order -> results are bit-reproducible run to run.
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+
+#pragma once
+#include "device.cuh"
+
+namespace vs {
+
+constexpr int FUSED_WARPS = 8;
+
+__host__ __device__ constexpr uint32_t prime_at(int d) {
+    constexpr uint32_t P[32] = {2,  3,  5,  7,  11, 13, 17, 19, 23, 29, 31, 37,  41,  43,  47,  53,
+                                59, 61, 67, 71, 73, 79, 83, 89, 97, 101, 103, 107, 109, 113, 127, 131};
+    return P[d];
+}
+
+__host__ __device__ constexpr int gram_tile_for(int M) {
+    int T = 1;
+    while (((M + T - 1) / T) * ((M + T - 1) / T + 1) / 2 > 32) ++T;
+    return T;
+}
+
+template <int K>
+struct FusedConst {            // kernel parameter -> constant bank; indexed with compile-time subscripts
+    double lb[K], wr[K];
+    uint32_t toff[K];          // offset of dimension d's terms inside the shared copy of the table
+    uint32_t nd[K];            // digits to sum for the largest index of the run
+    int scale_kind;
+    int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
+};
+
+// compile-time loop: fn(std::integral_constant<int, I>{}) for I in [0, N)
+template <int N, class Fn, int... I>
+__device__ __forceinline__ void static_for_impl(Fn &&fn, std::integer_sequence<int, I...>) {
+    (fn(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class Fn>
+__device__ __forceinline__ void static_for(Fn &&fn) {
+    static_for_impl<N>(fn, std::make_integer_sequence<int, N>{});
+}
+
+template <int N>
+__device__ __forceinline__ double tree_product(double (&s)[N]) {
+    if constexpr (N == 1) return s[0];
+    else {
+        constexpr int H = (N + 1) / 2;
+        double t[H];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) t[i] = s[2 * i] * s[2 * i + 1];
+        if constexpr (N % 2) t[H - 1] = s[N - 1];
+        return tree_product<H>(t);
+    }
+}
+
+// ---- register-resident functors --------------------------------------------------------------
+// Every design point is handed to the functor as its own k-vector of registers plus an opaque
+// scalar `tok` (value F::token, re-read from shared memory through a volatile load for every
+// point).  The functor must fold tok into its first operation on each coordinate.  Without it the
+// compiler notices that neighbouring points share k-1 coordinates and hoists the common
+// sub-expressions -- i.e. silently applies the separable shortcut -- and the generic path would
+// no longer evaluate each point (SURVEY.md §7 "honest flop accounting", §8d).  The token costs one
+// LDS per point and no arithmetic.
+//
+// g-function with the division hoisted: prod_c (|4x_c-2| + a_c)/(1+a_c) = C * prod_c (|4x_c-2| + a_c),
+// C = prod_c 1/(1+a_c).  Per factor: DFMA (tok*x - 2, tok = 4), DADD (|.| + a_c, a_c from the
+// constant bank), DMUL (tree product).
+template <int K>
+struct GFunctionReg {
+    double a[K];
+    double C;
+    static constexpr bool separable = true;
+    static constexpr double token = 4.0;
+    __device__ __forceinline__ double factor(int c, double x, double tok) const { return fabs(fma(tok, x, -2.0)) + a[c]; }
+    __device__ __forceinline__ double finish(double p) const { return C * p; }
+    __device__ __forceinline__ double operator()(const double (&x)[K], double tok) const {
+        double s[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) s[c] = factor(c, x[c], tok);
+        return C * tree_product<K>(s);
+    }
+};
+
+template <int K>
+struct IshigamiReg {
+    double A, B;
+    static constexpr bool separable = false;
+    static constexpr double token = 1.0;
+    __device__ __forceinline__ double operator()(const double (&x)[K], double tok) const {
+        double s0 = sin(x[0] * tok), s1 = sin(x[1] * tok), x2 = x[2] * tok;
+        double x22 = x2 * x2;
+        return s0 + A * s1 * s1 + B * (x22 * x22) * s0;
+    }
+};
+
+// ---- phase 1a: generate + scale the two base points A_i, B_i of the warp's 32 rows (lane = row) ----
+// emit(d, A_i[d], B_i[d]) is called once per coordinate, as soon as it is known (a warp that only
+// forwards the values to shared memory never holds the 2k-vector in registers).
+// Returns whether this lane's row exists (the last batch may be ragged).
+template <int K, int SCALE>
+__device__ __forceinline__ double scale_coord(const FusedConst<K> &fc, int d, double p) {
+    if constexpr (SCALE == VS_SCALE_LINEAR) return __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);     // scale.py:33, two roundings
+    else if constexpr (SCALE == VS_SCALE_POWER) return __dmul_rn(fc.lb[d], pow(fc.wr[d], p));       // scale.py:62
+    else return p;
+}
+
+// Halton digit sums of the two indices ia (A_i) and ib (B_i) for one GROUP of HG dimensions.  One run-time
+// digit loop per group carries 2*HG independent (index, sum) chains, which is what hides the integer-divide,
+// LDS and DADD latencies inside a single warp.  A dimension that runs out of digits keeps adding
+// T[last row][0] == +0.0, which is exact.  Group 0 also emits dimension 0: base 2, where every partial sum is
+// exact and the in-order digit sum is a bit reversal.
+constexpr int HG = 4;
+template <int K>
+__host__ __device__ constexpr int halton_groups() { return K > 1 ? (K - 1 + HG - 1) / HG : 1; }
+
+template <int K, int SCALE, int G, class Emit>
+__device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const double *__restrict__ terms, uint32_t ia, uint32_t ib,
+                                             Emit &&emit) {
+    if constexpr (G == 0)
+        emit(0, scale_coord<K, SCALE>(fc, 0, (double)__brev(ia) * 2.3283064365386962890625e-10),
+             scale_coord<K, SCALE>(fc, 0, (double)__brev(ib) * 2.3283064365386962890625e-10));
+    constexpr int D0 = 1 + G * HG;
+    if constexpr (D0 < K) {
+        constexpr int N = (K - D0) < HG ? (K - D0) : HG;
+        uint32_t ma[N], mb[N], off[N], offend[N];
+        double xa[N], xb[N];
+        int ndmax = 0;
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            ma[u] = ia;
+            mb[u] = ib;
+            xa[u] = 0.0;
+            xb[u] = 0.0;
+            off[u] = fc.toff[D0 + u];
+            offend[u] = fc.toff[D0 + u] + (fc.nd[D0 + u] - 1) * prime_at(D0 + u);
+            ndmax = ndmax > (int)fc.nd[D0 + u] ? ndmax : (int)fc.nd[D0 + u];
+        }
+        for (int j = 0; j < ndmax; ++j) {                 // least-significant digit first
+            static_for<N>([&](auto Uc) {
+                constexpr int U = decltype(Uc)::value;
+                constexpr uint32_t base = prime_at(D0 + U);
+                const double *Tt = terms + off[U];
+                uint32_t qa = ma[U] / base, qb = mb[U] / base;
+                xa[U] = __dadd_rn(xa[U], Tt[ma[U] - qa * base]);
+                xb[U] = __dadd_rn(xb[U], Tt[mb[U] - qb * base]);
+                ma[U] = qa;
+                mb[U] = qb;
+                off[U] = min(off[U] + base, offend[U]);
+            });
+        }
+#pragma unroll
+        for (int u = 0; u < N; ++u) emit(D0 + u, scale_coord<K, SCALE>(fc, D0 + u, xa[u]), scale_coord<K, SCALE>(fc, D0 + u, xb[u]));
+    }
+}
+
+template <int K, int SCALE, class Emit>
+__device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
+                                         uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
+    uint64_t r = bt * 32 + lane;
+    const bool valid = r < rows;
+    const uint64_t i = i_begin + (valid ? r : rows - 1);
+    const uint64_t pi = src.perm[i];
+    if (src.raw) {
+        const double *ra = src.raw + i * (uint64_t)K, *rb = src.raw + (src.n + pi) * (uint64_t)K;
+#pragma unroll
+        for (int d = 0; d < K; ++d) emit(d, scale_coord<K, SCALE>(fc, d, ra[d]), scale_coord<K, SCALE>(fc, d, rb[d]));
+    } else {
+        const uint32_t ia = (uint32_t)(src.start + i), ib = (uint32_t)(src.start + src.n + pi);
+        static_for<halton_groups<K>()>([&](auto Gc) { halton_group<K, SCALE, decltype(Gc)::value>(fc, terms, ia, ib, emit); });
+    }
+    return valid;
+}
+
+// One warp-uniform branch on the scale kind for the whole row (not one per coordinate).
+template <int K, class Emit>
+__device__ __forceinline__ bool gen_rows(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
+                                         uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
+    if (fc.scale_kind == VS_SCALE_IDENTITY) return gen_rows_impl<K, VS_SCALE_IDENTITY>(src, fc, terms, i_begin, rows, bt, lane, emit);
+    if (fc.scale_kind == VS_SCALE_LINEAR) return gen_rows_impl<K, VS_SCALE_LINEAR>(src, fc, terms, i_begin, rows, bt, lane, emit);
+    return gen_rows_impl<K, VS_SCALE_POWER>(src, fc, terms, i_begin, rows, bt, lane, emit);
+}
+
+// Generic evaluation of EG design points of one base row for a product-form functor (see eval_rows).
+constexpr int EG = 8;
+template <int K>
+__host__ __device__ constexpr int eval_groups() { return (2 + 2 * K + EG - 1) / EG; }
+
+template <int K, class F, int G, class YR>
+__device__ __forceinline__ void eval_group(const F &f, volatile double *tokp, const double (&a)[K], const double (&b)[K], bool valid,
+                                           const YR &Yrow, double &fA, double &fB) {
+    constexpr int M = 2 + 2 * K;
+    constexpr int P0 = G * EG;
+    constexpr int NP = (M - P0) < EG ? (M - P0) : EG;
+    double tk[NP], pr[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) tk[u] = *tokp;
+    static_for<K>([&](auto Cc) {
+        constexpr int C = decltype(Cc)::value;
+        static_for<NP>([&](auto Uc) {
+            constexpr int U = decltype(Uc)::value;
+            constexpr int P = P0 + U;
+            // point P: 0 = A_i, 1 = B_i, 2+J = B_i with column J from A_i, 2+K+J = A_i with column J from B_i
+            constexpr bool fromA = (P == 0) || (P >= 2 && P < 2 + K && C == P - 2) || (P >= 2 + K && C != P - 2 - K);
+            const double s_ = f.factor(C, fromA ? a[C] : b[C], tk[U]);
+            pr[U] = (C == 0) ? s_ : pr[U] * s_;
+        });
+    });
+    static_for<NP>([&](auto Uc) {
+        constexpr int U = decltype(Uc)::value;
+        constexpr int P = P0 + U;
+        const double v = f.finish(pr[U]);
+        if constexpr (P == 0) fA = v;
+        else if constexpr (P == 1) fB = v;
+        else Yrow[P] = valid ? v : 0.0;
+    });
+}
+
+struct YRef {                                  // value p of a lane's row lives at p[i * st]
+    double *p;
+    int st;
+    __device__ __forceinline__ double &operator[](int i) const { return p[i * st]; }
+};
+
+// ---- phase 1b: evaluate the functor on the 2+2k points of the lane's row; values go to Yrow ----
+template <int K, class F, bool SEPARABLE>
+__device__ __forceinline__ void eval_rows(const F &f, volatile double *tokp, const double (&a)[K], const double (&b)[K],
+                                          bool valid, double *__restrict__ Ybase, double shift, double &sA, double &qA,
+                                          double &sB, double &qB, const int ystride = 1) {
+    // value p of this lane's row lives at Ybase[p * ystride] (row-major tile: stride 1; p-major tile: stride = pitch)
+    const YRef Yrow{Ybase, ystride};
+    double fA, fB;
+    if constexpr (SEPARABLE && F::separable) {
+        // product-form shortcut: all 2+2k values from prefix/suffix products of the 2k factors
+        // (O(k) per row instead of O(k^2)).  Prefix pass parks prefix*factor in the tile, suffix
+        // pass completes it in place -- no k-long register arrays besides the factors.
+        double ga[K], gb[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) { ga[c] = f.factor(c, a[c], F::token); gb[c] = f.factor(c, b[c], F::token); }
+        double pa = 1.0, pb = 1.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            Yrow[2 + j] = pb * ga[j];                            // N_j[j]  = B with column j from A
+            Yrow[2 + K + j] = pa * gb[j];                        // N_nj[j] = A with column j from B
+            pa *= ga[j];
+            pb *= gb[j];
+        }
+        fA = f.finish(pa);
+        fB = f.finish(pb);
+        double sa = f.finish(1.0), sb = f.finish(1.0);           // suffix products carry the constant C
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            double vj = Yrow[2 + j] * sb, vn = Yrow[2 + K + j] * sa;
+            Yrow[2 + j] = valid ? vj : 0.0;
+            Yrow[2 + K + j] = valid ? vn : 0.0;
+            sa *= ga[j];
+            sb *= gb[j];
+        }
+    } else if constexpr (F::separable) {
+        // Generic path for product-form functors: every factor of every point is evaluated (no sharing between
+        // points -- each point has its own opaque token), but EG points advance together, factor by factor, each
+        // with a running product.  That gives the scheduler EG independent DMUL chains plus 2*EG independent
+        // DFMA/DADD per step (FP64 latency covered inside one warp) and needs no k-long temporary arrays.
+        fA = 0.0;
+        fB = 0.0;
+        static_for<eval_groups<K>()>([&](auto Gc) { eval_group<K, F, decltype(Gc)::value>(f, tokp, a, b, valid, Yrow, fA, fB); });
+    } else {
+        fA = f(a, *tokp);
+        fB = f(b, *tokp);
+        static_for<K>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value;
+            double xj[K], xn[K];
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+                xj[c] = (c == J) ? a[c] : b[c];                  // N_j[J]   (saltelli.py:119-123)
+                xn[c] = (c == J) ? b[c] : a[c];                  // N_nj[J]
+            }
+            double vj = f(xj, *tokp), vn = f(xn, *tokp);
+            Yrow[2 + J] = valid ? vj : 0.0;
+            Yrow[2 + K + J] = valid ? vn : 0.0;
+        });
+    }
+    Yrow[0] = valid ? fA : 0.0;
+    Yrow[1] = valid ? fB : 0.0;
+    if (valid) {
+        double dA = fA - shift, dB = fB - shift;
+        sA += dA;
+        qA = fma(dA, dA, qA);
+        sB += dB;
+        qB = fma(dB, dB, qB);
+    }
+}
+
+template <int K, class F, bool SEPARABLE>
+__device__ __forceinline__ void rows_phase(const SourceDev &src, const FusedConst<K> &fc, const F &f,
+                                           const double *__restrict__ terms, volatile double *tokp, uint64_t i_begin,
+                                           uint64_t rows, uint64_t bt, int lane, double *__restrict__ Yrow, double shift,
+                                           double &sA, double &qA, double &sB, double &qB) {
+    double a[K], b[K];
+    const bool valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+        a[d] = xa;
+        b[d] = xb;
+    });
+    eval_rows<K, F, SEPARABLE>(f, tokp, a, b, valid, Yrow, shift, sA, qA, sB, qB);
+}
+
+template <int K, class F, bool SECOND, bool SEPARABLE>
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 1)
+fused_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, const double *__restrict__ shift_ptr,
+             double *__restrict__ blockpart) {
+    constexpr int M = 2 + 2 * K;
+    constexpr int T = SECOND ? gram_tile_for(M) : 2;
+    constexpr int NT = (M + T - 1) / T;
+    constexpr int MP = (NT * T) % 2 ? NT * T : NT * T + 1;     // odd row pitch
+    constexpr int NTILES = SECOND ? NT * (NT + 1) / 2 : NT;    // first-order only: tile row 0 (fM_1, fM_2) x all columns
+    static_assert(SECOND ? NTILES <= 32 : true, "Gram does not fit one tile per lane");
+    constexpr int TPL = SECOND ? 1 : (NTILES + 31) / 32;
+
+    extern __shared__ double smem[];
+    double *terms = smem;                                           // shared copy of the Halton term table
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
+    volatile double *tokp = smem + nterms;                          // opaque functor token (see functors above)
+    double *Y = smem + nterms + 1 + (size_t)warp * 32 * MP;         // this warp's [32][MP] value tile
+    for (uint32_t e = threadIdx.x; e < nterms; e += blockDim.x) terms[e] = src.h.terms[e];
+    if (threadIdx.x == 0) *tokp = F::token;
+    // zero the padding columns once (never written again)
+    for (int e = lane; e < 32 * (MP - M); e += 32) Y[(e / (MP - M)) * MP + M + e % (MP - M)] = 0.0;
+    __syncthreads();
+
+    const double shift = *shift_ptr;
+    double sA = 0.0, qA = 0.0, sB = 0.0, qB = 0.0;
+    double acc[TPL][T][T];
+#pragma unroll
+    for (int q = 0; q < TPL; ++q)
+#pragma unroll
+        for (int x = 0; x < T; ++x)
+#pragma unroll
+            for (int y = 0; y < T; ++y) acc[q][x][y] = 0.0;
+    int tr[TPL], tc[TPL];
+#pragma unroll
+    for (int q = 0; q < TPL; ++q) {
+        int id = lane + 32 * q;
+        if (SECOND) tile_coords(id < NTILES ? id : 0, NT, tr[q], tc[q]);
+        else { tr[q] = 0; tc[q] = id < NTILES ? id : 0; }
+    }
+
+    const uint64_t rows = i_end - i_begin;
+    const uint64_t nbatch = (rows + 31) / 32;
+    const uint64_t wstride = (uint64_t)gridDim.x * FUSED_WARPS;
+    for (uint64_t bt = (uint64_t)blockIdx.x * FUSED_WARPS + warp; bt < nbatch; bt += wstride) {
+        rows_phase<K, F, SEPARABLE>(src, fc, f, terms, tokp, i_begin, rows, bt, lane, Y + lane * MP, shift, sA, qA, sB, qB);
+        __syncwarp();
+        // ------------------------------ phase 2: lane = Gram tile ------------------------------
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const double *row = Y + rr * MP;
+#pragma unroll
+            for (int q = 0; q < TPL; ++q) {
+                double ta[T], tb[T];
+#pragma unroll
+                for (int x = 0; x < T; ++x) { ta[x] = row[tr[q] * T + x]; tb[x] = row[tc[q] * T + x]; }
+                if constexpr (SECOND) {
+#pragma unroll
+                    for (int x = 0; x < T; ++x)
+#pragma unroll
+                        for (int y = 0; y < T; ++y) acc[q][x][y] = fma(ta[x], tb[y], acc[q][x][y]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 2; ++x)                       // rows fM_1, fM_2 only (T == 2)
+#pragma unroll
+                        for (int y = 0; y < T; ++y) acc[q][x][y] = fma(ta[x], tb[y], acc[q][x][y]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- combine warps in warp order through shared memory, then write this CTA's partial ----
+    __syncthreads();
+    constexpr int TT = T * T;
+    double *red = smem;                                   // [TPL*32][TT] + 4
+    sA = warp_sum(sA); qA = warp_sum(qA); sB = warp_sum(sB); qB = warp_sum(qB);
+    for (int w = 0; w < FUSED_WARPS; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int q = 0; q < TPL; ++q)
+#pragma unroll
+                for (int x = 0; x < T; ++x)
+#pragma unroll
+                    for (int y = 0; y < T; ++y) {
+                        double *p = red + ((size_t)(q * 32 + lane)) * TT + x * T + y;
+                        *p = (w == 0) ? acc[q][x][y] : *p + acc[q][x][y];
+                    }
+            if (lane == 0) {
+                double *s4 = red + (size_t)TPL * 32 * TT;
+                if (w == 0) { s4[0] = sA; s4[1] = sB; s4[2] = qA; s4[3] = qB; }
+                else { s4[0] += sA; s4[1] += sB; s4[2] += qA; s4[3] += qB; }
+            }
+        }
+        __syncthreads();
+    }
+    constexpr int PER_BLOCK = TPL * 32 * TT + 4;
+    for (int e = threadIdx.x; e < PER_BLOCK; e += blockDim.x) blockpart[(size_t)blockIdx.x * PER_BLOCK + e] = red[e];
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Warp specialisation helpers.  E-warps run phase 1 only (generation + evaluation, no Gram
+// accumulators -> more warps per SM); S-warps run the Gram update only.  S-warp s serves the E-warps
+// with the same warp id mod 4, i.e. the ones that share its SM sub-partition and FP64 pipe.  Tiles
+// are handed over through full/empty mbarrier pairs (producer: __syncwarp + one arrive; consumer:
+// try_wait.parity); there is no CTA-wide barrier inside the loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_S = 4;                       // one S-warp per SM sub-partition
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of spinning
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-role variant with the Gram update on the FP64 tensor path (DMMA, mma.sync m8n8k4.f64).
+// Measured on B200 (profiles/r01_fp64_pipes_microbench.txt): DMMA and DFMA share one 36-37 TFLOP/s
+// FP64 datapath, so DMMA adds no flops -- what it removes is shared-memory traffic and issue slots:
+// the register-tile SYRK needs 12 LDS.64 per row per lane (768 wavefronts per 32-row batch, and the
+// LSU pipe is shared by the four sub-partitions), the tensor path needs 6 fragment loads per FOUR
+// rows (96 wavefronts per batch) and 168 instead of 1152 issue slots.
+//   Y tile is p-major here: Yt[p][row] with pitch 36 -> E-warp stores are unit-stride, and the
+//   fragment  f_P = Yt[8P + lane/4][r0 + lane%4]  is both the A (row) and the B (col) operand of
+//   G[P][Q] += Y[r0..r0+4, P]^T Y[r0..r0+4, Q]  and loads conflict-free in two wavefronts.
+//   M is padded to NB = ceil(M/8) blocks (rows M..8NB-1 of the tile stay zero).
+// ---------------------------------------------------------------------------------------------
+constexpr int YT_PITCH = 36;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int K, class F, bool SEPARABLE, int EPS, int NBUF>
+__global__ void __launch_bounds__((EPS + 1) * WS_S * 32, 1)
+fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, const double *__restrict__ shift_ptr,
+                 double *__restrict__ blockpart) {
+    constexpr int WS_E = EPS * WS_S;
+    constexpr int M = 2 + 2 * K;
+    constexpr int NB = (M + 7) / 8;                     // 8-wide blocks
+    constexpr int MPAD = NB * 8;
+    constexpr int NTL = NB * (NB + 1) / 2;              // upper-triangular 8x8 tiles
+    constexpr int TILE = MPAD * YT_PITCH;               // doubles per Y tile
+
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
+    double *terms = smem;
+    volatile double *tokp = smem + nterms;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + nterms + 1);        // full[WS_E][NBUF], empty[WS_E][NBUF]
+    double *tiles = smem + nterms + 1 + 2 * NBUF * WS_E;                      // [WS_E][NBUF][TILE]
+    for (uint32_t e = threadIdx.x; e < nterms; e += blockDim.x) terms[e] = src.h.terms[e];
+    for (int e = threadIdx.x; e < WS_E * NBUF * TILE; e += blockDim.x) tiles[e] = 0.0;
+    if (threadIdx.x == 0) {
+        *tokp = F::token;
+        for (int b = 0; b < 2 * NBUF * WS_E; ++b) mbar_init(bars + b, 1);
+    }
+    __syncthreads();
+    auto full_bar = [&](int e, int slot) { return bars + (e * NBUF + slot); };
+    auto empty_bar = [&](int e, int slot) { return bars + NBUF * WS_E + (e * NBUF + slot); };
+
+    const uint64_t rows = i_end - i_begin;
+    const uint64_t nbatch = (rows + 31) / 32;
+    const uint64_t G = (uint64_t)gridDim.x * WS_E;
+    auto count_of = [&](int e) -> uint64_t {
+        uint64_t g = (uint64_t)blockIdx.x * WS_E + e;
+        return g < nbatch ? (nbatch - g + G - 1) / G : 0;
+    };
+    double sA = 0.0, qA = 0.0, sB = 0.0, qB = 0.0;
+    double acc[NTL][2];
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+
+    if (warp >= WS_S) {
+        // ------------------------------------ E-warp ------------------------------------
+        const int e = warp - WS_S;
+        const double shift = *shift_ptr;
+        const uint64_t cnt = count_of(e);
+        uint64_t bt = (uint64_t)blockIdx.x * WS_E + e;
+        for (uint64_t it = 0; it < cnt; ++it, bt += G) {
+            const int slot = (int)(it % NBUF);
+            double a[K], b[K];
+            bool valid = bt * 32 + lane < rows;
+            if (fc.debug & 1) {
+#pragma unroll
+                for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
+            } else {
+                valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+                    a[d] = xa;
+                    b[d] = xb;
+                });
+            }
+            mbar_wait(empty_bar(e, slot), (uint32_t)(((it / NBUF) & 1) ^ 1));
+            double *Y = tiles + ((size_t)e * NBUF + slot) * TILE;
+            if (fc.debug & 2) {
+#pragma unroll
+                for (int d = 0; d < K; ++d) { Y[lane + (2 + d) * YT_PITCH] = a[d]; Y[lane + (2 + K + d) * YT_PITCH] = b[d]; }
+            } else {
+                eval_rows<K, F, SEPARABLE>(f, tokp, a, b, valid, Y + lane, shift, sA, qA, sB, qB, YT_PITCH);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(e, slot));
+        }
+    } else {
+        // ------------------------------------ S-warp ------------------------------------
+        uint64_t cn[EPS], cmax = 0;
+#pragma unroll
+        for (int h = 0; h < EPS; ++h) {
+            cn[h] = count_of(warp + h * WS_S);
+            cmax = cn[h] > cmax ? cn[h] : cmax;
+        }
+        const int foff = (lane >> 2) * YT_PITCH + (lane & 3);   // fragment element of this lane inside an 8-row block
+        for (uint64_t it = 0; it < cmax; ++it) {
+            const int slot = (int)(it % NBUF);
+            const uint32_t par = (uint32_t)((it / NBUF) & 1);
+#pragma unroll
+            for (int h = 0; h < EPS; ++h) {
+                const int e = warp + h * WS_S;
+                if (it >= cn[h]) continue;
+                mbar_wait(full_bar(e, slot), par);
+                const double *Y = tiles + ((size_t)e * NBUF + slot) * TILE + foff;
+#pragma unroll 2
+                for (int r0 = 0; r0 < 32; r0 += 4) {
+                    double fr[NB];
+#pragma unroll
+                    for (int P = 0; P < NB; ++P) fr[P] = Y[P * 8 * YT_PITCH + r0];
+                    int t = 0;
+#pragma unroll
+                    for (int P = 0; P < NB; ++P)
+#pragma unroll
+                        for (int Q = P; Q < NB; ++Q, ++t) dmma_m8n8k4(acc[t][0], acc[t][1], fr[P], fr[Q]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(e, slot));
+            }
+        }
+    }
+
+    // ---- combine: every S-warp drops its C fragments into a dense MPAD x MPAD image, summed in S-warp order ----
+    __syncthreads();
+    double *img = smem;                                   // [WS_S][MPAD*MPAD] then [WS_E][4]
+    double *sums = img + (size_t)WS_S * MPAD * MPAD;
+    if (warp < WS_S) {
+        double *mine = img + (size_t)warp * MPAD * MPAD;
+        int t = 0;
+#pragma unroll
+        for (int P = 0; P < NB; ++P)
+#pragma unroll
+            for (int Q = P; Q < NB; ++Q, ++t) {
+                const int row = 8 * P + (lane >> 2), col = 8 * Q + 2 * (lane & 3);   // C fragment: (lane/4, 2*(lane%4)+{0,1})
+                mine[row * MPAD + col] = acc[t][0];
+                mine[row * MPAD + col + 1] = acc[t][1];
+            }
+    } else {
+        sA = warp_sum(sA); qA = warp_sum(qA); sB = warp_sum(sB); qB = warp_sum(qB);
+        if (lane == 0) {
+            double *s4 = sums + (warp - WS_S) * 4;
+            s4[0] = sA; s4[1] = sB; s4[2] = qA; s4[3] = qB;
+        }
+    }
+    __syncthreads();
+    constexpr int PER_BLOCK = MPAD * MPAD + 4;
+    double *bp = blockpart + (size_t)blockIdx.x * PER_BLOCK;
+    for (int e = threadIdx.x; e < MPAD * MPAD; e += blockDim.x) {
+        const int row = e / MPAD, col = e % MPAD;
+        double v = 0.0;
+        if (row / 8 <= col / 8) {
+#pragma unroll
+            for (int w = 0; w < WS_S; ++w) v += img[(size_t)w * MPAD * MPAD + e];
+        }
+        bp[e] = v;
+    }
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int w = 0; w < WS_E; ++w) v += sums[w * 4 + threadIdx.x];
+        bp[MPAD * MPAD + threadIdx.x] = v;
+    }
+}
+
+// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector, CTA order.
+static __global__ void __launch_bounds__(256) dense_scatter_kernel(int m, int mpad, int nblocks, const double *__restrict__ blockpart,
+                                                            double *__restrict__ partials) {
+    const size_t per_block = (size_t)mpad * mpad + 4;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < 4) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + (size_t)mpad * mpad + e];
+        partials[e] = s;
+    }
+    if (e >= mpad * mpad) return;
+    const int p = e / mpad, q = e % mpad;
+    if (p >= m || q >= m || p > q) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + e];
+    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = s;
+}
+
+// f(M_1[0]): the common shift for the variance sums (identical on every rank).
+template <int K, class F>
+__global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double x[K];
+    for (int d = 0; d < K; ++d) {
+        double p = src.raw ? src.raw[d] : halton_coord(src.h, d, (uint32_t)src.start);
+        if (fc.scale_kind == VS_SCALE_LINEAR) p = __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);
+        else if (fc.scale_kind == VS_SCALE_POWER) p = __dmul_rn(fc.lb[d], pow(fc.wr[d], p));
+        x[d] = p;
+    }
+    *out = f(x, F::token);
+}
+
+template <int K, class F, bool SECOND, bool SEPARABLE>
+static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &fc, const F &f, uint64_t i_begin, uint64_t i_end,
+                          double *partials) {
+    constexpr int M = 2 + 2 * K;
+    constexpr int T = SECOND ? gram_tile_for(M) : 2;
+    constexpr int NT = (M + T - 1) / T;
+    constexpr int MP = (NT * T) % 2 ? NT * T : NT * T + 1;
+    constexpr int NTILES = SECOND ? NT * (NT + 1) / 2 : NT;
+    constexpr int TPL = SECOND ? 1 : (NTILES + 31) / 32;
+    constexpr int PER_BLOCK = TPL * 32 * T * T + 4;
+    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
+    const uint64_t rows = i_end - i_begin;
+    const uint64_t nbatch = (rows + 31) / 32;
+    // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
+    //   1 = single-role warps, register-tile Gram (also the first-order-only kernel)
+    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram (default)   6 = same with 3 E-warps per S-warp
+    int variant = SECOND ? 5 : 1;
+    if (const char *ev = getenv("VS_FUSED_VARIANT")) variant = SECOND ? atoi(ev) : 1;
+    if constexpr (SECOND) {
+        if (variant == 5 || variant == 6) {
+            constexpr int NBk = (M + 7) / 8, MPADk = NBk * 8;
+            const int eps = variant == 6 ? 3 : 2;
+            uint64_t wantd = (nbatch + eps * WS_S - 1) / (eps * WS_S);
+            int gridd = (int)(wantd < (uint64_t)c->sm_count ? wantd : (uint64_t)c->sm_count);
+            if (gridd < 1) gridd = 1;
+            const size_t per_block = (size_t)MPADk * MPADk + 4;
+            VS_TRY(ensure(c, c->block_buf, (size_t)gridd * per_block * sizeof(double)));
+            VS_TRY(ensure(c, c->misc_buf, 64));
+            shift_kernel<K, F><<<1, 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
+            c->launches++;
+            size_t smem_run = ((size_t)nterms + 1 + 2 * eps * WS_S + (size_t)eps * WS_S * MPADk * YT_PITCH) * sizeof(double);
+            size_t smem_red = ((size_t)WS_S * MPADk * MPADk + 4 * eps * WS_S) * sizeof(double);
+            size_t smem = smem_run > smem_red ? smem_run : smem_red;
+            VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
+            auto kern = variant == 6 ? fused_wsd_kernel<K, F, SEPARABLE, 3, 1> : fused_wsd_kernel<K, F, SEPARABLE, 2, 1>;
+            VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            time_begin(c);
+            kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, (const double *)c->misc_buf.p,
+                                                                    (double *)c->block_buf.p);
+            time_end(c);
+            c->launches++;
+            VS_CUDA(cudaGetLastError());
+            const int plen = (int)vs_partials_len(K, 1);
+            VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
+            dense_scatter_kernel<<<(MPADk * MPADk + 255) / 256, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
+                                                                                   partials);
+            c->launches++;
+            VS_CUDA(cudaGetLastError());
+            return VS_OK;
+        }
+    }
+    const int ewarps = FUSED_WARPS;
+    uint64_t want = (nbatch + ewarps - 1) / ewarps;
+    int grid = (int)(want < (uint64_t)c->sm_count ? want : (uint64_t)c->sm_count);
+    if (grid < 1) grid = 1;
+    VS_TRY(ensure(c, c->block_buf, (size_t)grid * PER_BLOCK * sizeof(double)));
+    VS_TRY(ensure(c, c->misc_buf, 64));
+    shift_kernel<K, F><<<1, 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
+    c->launches++;
+    {
+        size_t smem_run = ((size_t)nterms + 1 + (size_t)FUSED_WARPS * 32 * MP) * sizeof(double);
+        size_t smem_red = ((size_t)TPL * 32 * T * T + 4) * sizeof(double);
+        size_t smem = smem_run > smem_red ? smem_run : smem_red;
+        VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
+        auto kern = fused_kernel<K, F, SECOND, SEPARABLE>;
+        VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        time_begin(c);
+        kern<<<grid, FUSED_WARPS * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, (const double *)c->misc_buf.p,
+                                                          (double *)c->block_buf.p);
+        time_end(c);
+    }
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    GramGeom g{};
+    g.m = M; g.l = 1; g.T = T; g.nt = NT; g.mp = MP;
+    g.tr_max = SECOND ? NT : 1;
+    g.ntiles = NTILES; g.LG = 32; g.RG = 1; g.R = 32; g.passes = TPL;
+    return launch_gram_scatter(c, g, grid, (const double *)c->block_buf.p, partials, (int)vs_partials_len(K, 1));
+}
+
+template <int K>
+static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedConst<K> &fc) {
+    fc.scale_kind = s.kind;
+    fc.debug = getenv("VS_DEBUG_SKIP") ? atoi(getenv("VS_DEBUG_SKIP")) : 0;
+    double h[2 * K];
+    if (s.kind != VS_SCALE_IDENTITY) {
+        VS_CUDA(cudaMemcpyAsync(h, s.lb, sizeof(double) * 2 * K, cudaMemcpyDeviceToHost, c->stream));   // lb | wr are contiguous
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    for (int d = 0; d < K; ++d) {
+        fc.lb[d] = s.kind != VS_SCALE_IDENTITY ? h[d] : 0.0;
+        fc.wr[d] = s.kind != VS_SCALE_IDENTITY ? h[K + d] : 1.0;
+        fc.toff[d] = 0;
+        fc.nd[d] = 0;
+    }
+    if (!src.raw) {
+        uint32_t off = 0;
+        for (int d = 0; d < K; ++d) {
+            fc.toff[d] = off;
+            uint32_t need = 0;                                   // digits of this run's largest index
+            for (uint64_t m = src.start + 2 * src.n - 1; m > 0; m /= prime_at(d)) ++need;
+            fc.nd[d] = need;
+            off += c->halton.ndigits[d] * prime_at(d);         // layout of the (possibly longer) cached table
+        }
+        // the cached table may have more digits than this run needs: its layout is what matters
+        VS_REQUIRE(off == src.h.total_terms, VS_ERR_ARG, "Halton table layout mismatch (%u vs %u)", off, src.h.total_terms);
+    }
+    return VS_OK;
+}
+
+template <int K>
+static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin, uint64_t i_end,
+                      int flags, double *partials) {
+    FusedConst<K> fc;
+    VS_TRY(fill_const<K>(c, src, s, fc));
+    const bool second = flags & VS_FLAG_SECOND_ORDER, sep = flags & VS_FLAG_SEPARABLE;
+    double hp[3 * K + 2];
+    VS_CUDA(cudaMemcpyAsync(hp, o.params, sizeof(double) * o.n_params, cudaMemcpyDeviceToHost, c->stream));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    if (o.id == VS_OBJ_GFUNCTION) {
+        GFunctionReg<K> f;
+        f.C = 1.0;
+        for (int d = 0; d < K; ++d) { f.a[d] = hp[d]; f.C *= hp[K + d]; }
+        if (second) {
+            if (sep) return launch_fused_t<K, GFunctionReg<K>, true, true>(c, src, fc, f, i_begin, i_end, partials);
+            return launch_fused_t<K, GFunctionReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials);
+        }
+        if (sep) return launch_fused_t<K, GFunctionReg<K>, false, true>(c, src, fc, f, i_begin, i_end, partials);
+        return launch_fused_t<K, GFunctionReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials);
+    }
+    if constexpr (K == 3) {
+        if (o.id == VS_OBJ_ISHIGAMI) {
+            IshigamiReg<K> f{hp[0], hp[1]};
+            if (second) return launch_fused_t<K, IshigamiReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials);
+            return launch_fused_t<K, IshigamiReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials);
+        }
+    }
+    set_error("objective %d has no fused kernel for k=%d", o.id, K);
+    return VS_ERR_UNSUPPORTED;
+}
+
+}  // namespace vs

@@ -1,0 +1,15 @@
+// One translation unit per compile-time k of the fused pipeline (nvcc -DVS_FUSED_K=<k>, see Makefile).
+#include "fused_impl.cuh"
+
+#ifndef VS_FUSED_K
+#error "compile with -DVS_FUSED_K=<k>"
+#endif
+#define VS_CAT2(a, b) a##b
+#define VS_CAT(a, b) VS_CAT2(a, b)
+
+namespace vs {
+int VS_CAT(launch_fused_k, VS_FUSED_K)(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
+                                       uint64_t i_end, int flags, double *partials) {
+    return dispatch_k<VS_FUSED_K>(c, src, s, o, i_begin, i_end, flags, partials);
+}
+}  // namespace vs
