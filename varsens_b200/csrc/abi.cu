@@ -250,7 +250,10 @@ extern "C" int vs_fused_partials(vs_ctx *c, int k, uint64_t n, uint64_t discard,
     VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, i_begin,
                               i_end, flags, (double *)o.dev));
     VS_TRY(o.end());
-    if (partials_mem == VS_MEM_DEVICE) VS_CUDA(cudaStreamSynchronize(c->stream));
+    // all-device call: only enqueued (the caller's next op on the same stream, e.g. the all-reduce, orders after it);
+    // with a host input the staged copy must have left the caller's buffer before we return
+    if (partials_mem == VS_MEM_DEVICE && (perm_mem == VS_MEM_HOST || (raw && raw_mem == VS_MEM_HOST)))
+        VS_CUDA(cudaStreamSynchronize(c->stream));
     return VS_OK;
 }
 

@@ -14,6 +14,7 @@
 //            each of the 32 rows 2T broadcast shared loads feed T^2 DFMA.  G holds every sum the
 //            estimators need.  Shifted sums for var_y stay lane-local in phase 1.
 // Warps, then CTAs, are combined in a fixed order -> results are bit-reproducible run to run.
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <utility>
@@ -42,6 +43,10 @@ struct FusedConst {            // kernel parameter -> constant bank; indexed wit
     double lb[K], wr[K];
     uint32_t toff[K];          // offset of dimension d's terms inside the shared copy of the table
     uint32_t nd[K];            // digits to sum for the largest index of the run
+    uint32_t ndc[K];           // digit rows the cached global table holds per dimension (layout: toff)
+    int small_index;           // every Halton index of the run is < 2^29
+    int alternate;             // E-warp teams alternate generate / evaluate phases (see fused_wsd_kernel)
+    long long *trace;          // profiling only (VS_TRACE): per-warp clock stamps of CTA 0, else nullptr
     int scale_kind;
     int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
 };
@@ -76,7 +81,8 @@ __device__ __forceinline__ double tree_product(double (&s)[N]) {
 // compiler notices that neighbouring points share k-1 coordinates and hoists the common
 // sub-expressions -- i.e. silently applies the separable shortcut -- and the generic path would
 // no longer evaluate each point (SURVEY.md §7 "honest flop accounting", §8d).  The token costs one
-// LDS per point and no arithmetic.
+// LDS per point and no arithmetic.  (Kernel-parameter tokens and register-only tokens were tried: with either,
+// ptxas interleaves only 2-3 design points in the evaluation and the kernel gets 10-15 % slower.)
 //
 // g-function with the division hoisted: prod_c (|4x_c-2| + a_c)/(1+a_c) = C * prod_c (|4x_c-2| + a_c),
 // C = prod_c 1/(1+a_c).  Per factor: DFMA (tok*x - 2, tok = 4), DADD (|.| + a_c, a_c from the
@@ -120,11 +126,66 @@ __device__ __forceinline__ double scale_coord(const FusedConst<K> &fc, int d, do
     else return p;
 }
 
-// Halton digit sums of the two indices ia (A_i) and ib (B_i) for one GROUP of HG dimensions.  One run-time
-// digit loop per group carries 2*HG independent (index, sum) chains, which is what hides the integer-divide,
-// LDS and DADD latencies inside a single warp.  A dimension that runs out of digits keeps adding
-// T[last row][0] == +0.0, which is exact.  Group 0 also emits dimension 0: base 2, where every partial sum is
-// exact and the in-order digit sum is a bit reversal.
+// ---- Halton digit sums --------------------------------------------------------------------------------------
+// Shared-memory copy of the term table in a FIXED layout: dimension d (base b) owns ndmax32(b) rows of b doubles
+// at double offset foff(d); row j holds digit / b^(j+1).  Fixed row counts (enough for any 32-bit index) make
+// every row address a compile-time immediate of the LDS.  Rows the cached global table does not have are 0.0
+// (they are only ever read at digit 0, whose term is 0.0 anyway).
+__host__ __device__ constexpr int ndmax32(uint32_t b) {
+    int c = 0;
+    for (uint64_t m = 0xFFFFFFFFull; m > 0; m /= b) ++c;
+    return c;
+}
+__host__ __device__ constexpr uint32_t foff(int d) {          // dimension 0 (base 2) needs no table
+    uint32_t s = 0;
+    for (int e = 1; e < d; ++e) s += prime_at(e) * (uint32_t)ndmax32(prime_at(e));
+    return s;
+}
+// First digit position from which m * 8b < 2^32 holds for ANY 32-bit index (m_j < 2^32 / b^j): b^(j-1) >= 8.
+__host__ __device__ constexpr int jfast(uint32_t b) {
+    int j = 1;
+    for (uint64_t p = 1; p < 8; p *= b) ++j;
+    return j;
+}
+
+template <int K>
+__device__ __forceinline__ void load_fixed_table(double *__restrict__ dst, const HaltonDev &h, const FusedConst<K> &fc) {
+    static_for<K>([&](auto Dc) {
+        constexpr int D = decltype(Dc)::value;
+        if constexpr (D >= 1) {
+            constexpr uint32_t b = prime_at(D);
+            constexpr int rows = ndmax32(b);
+            const uint32_t have = fc.ndc[D] * b;                // doubles the cached global table holds for this dimension
+            for (uint32_t e = threadIdx.x; e < rows * b; e += blockDim.x) dst[foff(D) + e] = e < have ? h.terms[fc.toff[D] + e] : 0.0;
+        }
+    });
+}
+
+// One digit of (m -> m / b, term of m mod b) for two chains.  The in-order additions are __dadd_rn (no
+// re-association, no contraction).  FAST form (needs m * 8b < 2^32, proved and brute-forced in
+// tools/check_fastdiv.py): c = ceil(2^32 / b);  m*c as a 64-bit product gives q = hi and, from the low word,
+// 8*(m mod b) = umulhi(lo, 8b) -- two multiplies, no shift, no subtraction, and the result is already the byte
+// offset into the row.  GENERAL form: the compiler's division by a constant.
+template <uint32_t B, bool FAST>
+__device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *__restrict__ row) {
+    uint32_t off8;
+    if constexpr (FAST) {
+        constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
+        const uint64_t w = (uint64_t)m * C;
+        off8 = __umulhi((uint32_t)w, 8u * B);
+        m = (uint32_t)(w >> 32);
+    } else {
+        const uint32_t q = m / B;
+        off8 = (m - q * B) * 8u;
+        m = q;
+    }
+    x = __dadd_rn(x, *reinterpret_cast<const double *>(row + off8));
+}
+
+// Halton digit sums of the two indices ia (A_i) and ib (B_i) for one GROUP of HG dimensions: 2*HG independent
+// (index, sum) chains advance together, least-significant digit first; the group stops after the largest digit
+// count it needs for this run (warp-uniform).  Group 0 also emits dimension 0: base 2, where every partial sum
+// is exact and the in-order digit sum is a bit reversal.
 constexpr int HG = 4;
 template <int K>
 __host__ __device__ constexpr int halton_groups() { return K > 1 ? (K - 1 + HG - 1) / HG : 1; }
@@ -138,7 +199,8 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
     constexpr int D0 = 1 + G * HG;
     if constexpr (D0 < K) {
         constexpr int N = (K - D0) < HG ? (K - D0) : HG;
-        uint32_t ma[N], mb[N], off[N], offend[N];
+        constexpr int JMAX = ndmax32(prime_at(D0));         // the smallest base of the group has the most digits
+        uint32_t ma[N], mb[N];
         double xa[N], xb[N];
         int ndmax = 0;
 #pragma unroll
@@ -147,23 +209,40 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
             mb[u] = ib;
             xa[u] = 0.0;
             xb[u] = 0.0;
-            off[u] = fc.toff[D0 + u];
-            offend[u] = fc.toff[D0 + u] + (fc.nd[D0 + u] - 1) * prime_at(D0 + u);
             ndmax = ndmax > (int)fc.nd[D0 + u] ? ndmax : (int)fc.nd[D0 + u];
         }
-        for (int j = 0; j < ndmax; ++j) {                 // least-significant digit first
-            static_for<N>([&](auto Uc) {
-                constexpr int U = decltype(Uc)::value;
-                constexpr uint32_t base = prime_at(D0 + U);
-                const double *Tt = terms + off[U];
-                uint32_t qa = ma[U] / base, qb = mb[U] / base;
-                xa[U] = __dadd_rn(xa[U], Tt[ma[U] - qa * base]);
-                xb[U] = __dadd_rn(xb[U], Tt[mb[U] - qb * base]);
-                ma[U] = qa;
-                mb[U] = qb;
-                off[U] = min(off[U] + base, offend[U]);
-            });
-        }
+        const char *tb = reinterpret_cast<const char *>(terms);
+        const bool small = fc.small_index != 0;             // every index of the run < 2^29: FAST from digit 1 on
+        // All JMAX digit positions are executed unconditionally: one straight-line block per group, so the
+        // scheduler can run the index chains ahead and keep many table loads in flight (with a branch per digit
+        // the loads of digit j+1 could not be hoisted over the additions of digit j and every digit paid a full,
+        // queue-inflated LDS latency).  Positions beyond the run's digit count see m == 0 and add +0.0 (exact).
+        (void)ndmax;
+        static_for<JMAX>([&](auto Jc) {
+            constexpr int J = decltype(Jc)::value;
+            {
+                static_for<N>([&](auto Uc) {
+                    constexpr int U = decltype(Uc)::value;
+                    constexpr uint32_t B = prime_at(D0 + U);
+                    if constexpr (J < ndmax32(B)) {
+                        const char *row = tb + (size_t)(foff(D0 + U) + J * B) * 8;
+                        if constexpr (J == 0) {
+                            digit_step<B, false>(ma[U], xa[U], row);
+                            digit_step<B, false>(mb[U], xb[U], row);
+                        } else if constexpr (J >= jfast(B)) {
+                            digit_step<B, true>(ma[U], xa[U], row);
+                            digit_step<B, true>(mb[U], xb[U], row);
+                        } else if (small) {
+                            digit_step<B, true>(ma[U], xa[U], row);
+                            digit_step<B, true>(mb[U], xb[U], row);
+                        } else {
+                            digit_step<B, false>(ma[U], xa[U], row);
+                            digit_step<B, false>(mb[U], xb[U], row);
+                        }
+                    }
+                });
+            }
+        });
 #pragma unroll
         for (int u = 0; u < N; ++u) emit(D0 + u, scale_coord<K, SCALE>(fc, D0 + u, xa[u]), scale_coord<K, SCALE>(fc, D0 + u, xb[u]));
     }
@@ -334,10 +413,10 @@ fused_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_
     extern __shared__ double smem[];
     double *terms = smem;                                           // shared copy of the Halton term table
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
-    volatile double *tokp = smem + nterms;                          // opaque functor token (see functors above)
+    const uint32_t nterms = src.raw ? 0u : foff(K);
+    volatile double *tokp = smem + nterms;                          // opaque functor token (see the functors)
     double *Y = smem + nterms + 1 + (size_t)warp * 32 * MP;         // this warp's [32][MP] value tile
-    for (uint32_t e = threadIdx.x; e < nterms; e += blockDim.x) terms[e] = src.h.terms[e];
+    if (nterms) load_fixed_table<K>(terms, src.h, fc);
     if (threadIdx.x == 0) *tokp = F::token;
     // zero the padding columns once (never written again)
     for (int e = lane; e < 32 * (MP - M); e += 32) Y[(e / (MP - M)) * MP + M + e % (MP - M)] = 0.0;
@@ -461,6 +540,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 //   G[P][Q] += Y[r0..r0+4, P]^T Y[r0..r0+4, Q]  and loads conflict-free in two wavefronts.
 //   M is padded to NB = ceil(M/8) blocks (rows M..8NB-1 of the tile stay zero).
 // ---------------------------------------------------------------------------------------------
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 constexpr int YT_PITCH = 36;
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
@@ -482,12 +564,12 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
+    const uint32_t nterms = src.raw ? 0u : foff(K);
     double *terms = smem;
-    volatile double *tokp = smem + nterms;
+    volatile double *tokp = smem + nterms;                                    // opaque functor token (see the functors)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + nterms + 1);        // full[WS_E][NBUF], empty[WS_E][NBUF]
     double *tiles = smem + nterms + 1 + 2 * NBUF * WS_E;                      // [WS_E][NBUF][TILE]
-    for (uint32_t e = threadIdx.x; e < nterms; e += blockDim.x) terms[e] = src.h.terms[e];
+    if (nterms) load_fixed_table<K>(terms, src.h, fc);
     for (int e = threadIdx.x; e < WS_E * NBUF * TILE; e += blockDim.x) tiles[e] = 0.0;
     if (threadIdx.x == 0) {
         *tokp = F::token;
@@ -515,10 +597,25 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         const double shift = *shift_ptr;
         const uint64_t cnt = count_of(e);
         uint64_t bt = (uint64_t)blockIdx.x * WS_E + e;
+        // Phase alternation between the two E-warp teams (team = e / WS_S; every sub-partition has one warp of each).
+        // Generation is bound by the SM-wide shared-memory pipe (random 8-byte table lookups cost 3-5 wavefronts
+        // each), evaluation by the per-sub-partition FP64 pipe.  Left alone, the E-warps drift into lock-step --
+        // a warp that generates while the others evaluate finds the LSU free, finishes early and catches up -- and
+        // then the two phases add up (clock stamps: 12.6k + 10.5k cycles per batch).  A named barrier over the E-warps
+        // after every phase pins team 0 to "generate" while team 1 "evaluates" and vice versa.
+        const bool alternate = (EPS == 2) && fc.alternate;
+        auto ebar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
+        const int team = e / WS_S;
+        const uint64_t bars_total = 2 * count_of(0) + 1;              // count_of(0) is the largest batch count in the CTA
+        uint64_t bars_done = 0;
+        if (alternate && team == 1) { ebar(); ++bars_done; }
         for (uint64_t it = 0; it < cnt; ++it, bt += G) {
             const int slot = (int)(it % NBUF);
             double a[K], b[K];
             bool valid = bt * 32 + lane < rows;
+            const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 64;
+            long long *trp = fc.trace + ((size_t)warp * 64 + (it < 64 ? it : 0)) * 4;
+            if (tr_on) trp[0] = clock64();
             if (fc.debug & 1) {
 #pragma unroll
                 for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
@@ -528,7 +625,10 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
                     b[d] = xb;
                 });
             }
+            if (tr_on) trp[1] = clock64();
+            if (alternate) { ebar(); ++bars_done; }
             mbar_wait(empty_bar(e, slot), (uint32_t)(((it / NBUF) & 1) ^ 1));
+            if (tr_on) trp[2] = clock64();
             double *Y = tiles + ((size_t)e * NBUF + slot) * TILE;
             if (fc.debug & 2) {
 #pragma unroll
@@ -537,8 +637,12 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
                 eval_rows<K, F, SEPARABLE>(f, tokp, a, b, valid, Y + lane, shift, sA, qA, sB, qB, YT_PITCH);
             }
             __syncwarp();
+            if (tr_on) trp[3] = clock64();
             if (lane == 0) mbar_arrive(full_bar(e, slot));
+            if (alternate) { ebar(); ++bars_done; }
         }
+        if (alternate)
+            for (; bars_done < bars_total; ++bars_done) ebar();       // keep the other team's barriers matched
     } else {
         // ------------------------------------ S-warp ------------------------------------
         uint64_t cn[EPS], cmax = 0;
@@ -555,7 +659,11 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
             for (int h = 0; h < EPS; ++h) {
                 const int e = warp + h * WS_S;
                 if (it >= cn[h]) continue;
+                const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 32;
+                long long *trp = fc.trace + ((size_t)warp * 64 + (it < 32 ? it * EPS + h : 0)) * 4;
+                if (tr_on) trp[0] = clock64();
                 mbar_wait(full_bar(e, slot), par);
+                if (tr_on) trp[1] = clock64();
                 const double *Y = tiles + ((size_t)e * NBUF + slot) * TILE + foff;
 #pragma unroll 2
                 for (int r0 = 0; r0 < 32; r0 += 4) {
@@ -569,6 +677,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
                         for (int Q = P; Q < NB; ++Q, ++t) dmma_m8n8k4(acc[t][0], acc[t][1], fr[P], fr[Q]);
                 }
                 __syncwarp();
+                if (tr_on) trp[2] = clock64();
                 if (lane == 0) mbar_arrive(empty_bar(e, slot));
             }
         }
@@ -657,7 +766,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     constexpr int NTILES = SECOND ? NT * (NT + 1) / 2 : NT;
     constexpr int TPL = SECOND ? 1 : (NTILES + 31) / 32;
     constexpr int PER_BLOCK = TPL * 32 * T * T + 4;
-    const uint32_t nterms = src.raw ? 0u : src.h.total_terms;
+    const uint32_t nterms = src.raw ? 0u : foff(K);
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
     // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
@@ -689,6 +798,19 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             time_end(c);
             c->launches++;
             VS_CUDA(cudaGetLastError());
+            if (fc.trace) {                                  // profiling only: dump CTA 0's clock stamps
+                std::vector<long long> h(16 * 64 * 4);
+                VS_CUDA(cudaMemcpyAsync(h.data(), fc.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+                VS_CUDA(cudaStreamSynchronize(c->stream));
+                if (FILE *fp = fopen(getenv("VS_TRACE"), "w")) {
+                    for (int w = 0; w < 16; ++w)
+                        for (int i = 0; i < 64; ++i) {
+                            const long long *r = &h[((size_t)w * 64 + i) * 4];
+                            if (r[0]) fprintf(fp, "%d %d %lld %lld %lld %lld\n", w, i, r[0], r[1], r[2], r[3]);
+                        }
+                    fclose(fp);
+                }
+            }
             const int plen = (int)vs_partials_len(K, 1);
             VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
             dense_scatter_kernel<<<(MPADk * MPADk + 255) / 256, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
@@ -731,16 +853,21 @@ template <int K>
 static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedConst<K> &fc) {
     fc.scale_kind = s.kind;
     fc.debug = getenv("VS_DEBUG_SKIP") ? atoi(getenv("VS_DEBUG_SKIP")) : 0;
-    double h[2 * K];
-    if (s.kind != VS_SCALE_IDENTITY) {
-        VS_CUDA(cudaMemcpyAsync(h, s.lb, sizeof(double) * 2 * K, cudaMemcpyDeviceToHost, c->stream));   // lb | wr are contiguous
-        VS_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    const double *h = s.host;                                   // lb | wr
     for (int d = 0; d < K; ++d) {
         fc.lb[d] = s.kind != VS_SCALE_IDENTITY ? h[d] : 0.0;
         fc.wr[d] = s.kind != VS_SCALE_IDENTITY ? h[K + d] : 1.0;
         fc.toff[d] = 0;
         fc.nd[d] = 0;
+        fc.ndc[d] = 0;
+    }
+    fc.small_index = 0;
+    fc.trace = nullptr;
+    fc.alternate = getenv("VS_ALTERNATE") ? atoi(getenv("VS_ALTERNATE")) : 0;
+    if (getenv("VS_TRACE")) {
+        VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
+        VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));
+        fc.trace = (long long *)c->dir_buf.p;
     }
     if (!src.raw) {
         uint32_t off = 0;
@@ -749,9 +876,11 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
             uint32_t need = 0;                                   // digits of this run's largest index
             for (uint64_t m = src.start + 2 * src.n - 1; m > 0; m /= prime_at(d)) ++need;
             fc.nd[d] = need;
+            fc.ndc[d] = c->halton.ndigits[d];
             off += c->halton.ndigits[d] * prime_at(d);         // layout of the (possibly longer) cached table
         }
         // the cached table may have more digits than this run needs: its layout is what matters
+        fc.small_index = (src.start + 2 * src.n - 1) < (1ull << 29) ? 1 : 0;
         VS_REQUIRE(off == src.h.total_terms, VS_ERR_ARG, "Halton table layout mismatch (%u vs %u)", off, src.h.total_terms);
     }
     return VS_OK;
@@ -763,9 +892,7 @@ static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const 
     FusedConst<K> fc;
     VS_TRY(fill_const<K>(c, src, s, fc));
     const bool second = flags & VS_FLAG_SECOND_ORDER, sep = flags & VS_FLAG_SEPARABLE;
-    double hp[3 * K + 2];
-    VS_CUDA(cudaMemcpyAsync(hp, o.params, sizeof(double) * o.n_params, cudaMemcpyDeviceToHost, c->stream));
-    VS_CUDA(cudaStreamSynchronize(c->stream));
+    const double *hp = o.host;
     if (o.id == VS_OBJ_GFUNCTION) {
         GFunctionReg<K> f;
         f.C = 1.0;

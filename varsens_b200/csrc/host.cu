@@ -149,7 +149,7 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
 
 int get_scale(vs_ctx *c, int k, const vs_scale *s, ScaleDev *out) {
     out->kind = VS_SCALE_IDENTITY;
-    out->lb = out->wr = nullptr;
+    out->lb = out->wr = out->host = nullptr;
     if (!s || s->kind == VS_SCALE_IDENTITY) return VS_OK;
     VS_REQUIRE(s->kind == VS_SCALE_LINEAR || s->kind == VS_SCALE_POWER, VS_ERR_ARG, "unknown scale kind %d", s->kind);
     VS_REQUIRE(s->lower && s->upper, VS_ERR_ARG, "scale bounds are NULL");
@@ -160,12 +160,18 @@ int get_scale(vs_ctx *c, int k, const vs_scale *s, ScaleDev *out) {
         h[d] = lo;
         h[k + d] = wr;
     }
-    VS_TRY(ensure(c, c->scale_buf, h.size() * sizeof(double)));
-    VS_CUDA(cudaMemcpyAsync(c->scale_buf.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    VS_CUDA(cudaStreamSynchronize(c->stream));   // h is a stack-lifetime vector
+    if (!(c->scale_kind_cached == s->kind && c->scale_k_cached == k && c->scale_host == h && c->scale_buf.p)) {
+        VS_CUDA(cudaStreamSynchronize(c->stream));   // a kernel in flight may still read the old descriptor
+        c->scale_host = h;
+        VS_TRY(ensure(c, c->scale_buf, h.size() * sizeof(double)));
+        VS_CUDA(cudaMemcpyAsync(c->scale_buf.p, c->scale_host.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->scale_kind_cached = s->kind;
+        c->scale_k_cached = k;
+    }
     out->kind = s->kind;
     out->lb = (const double *)c->scale_buf.p;
     out->wr = out->lb + k;
+    out->host = c->scale_host.data();
     return VS_OK;
 }
 
@@ -196,12 +202,17 @@ int get_objective(vs_ctx *c, int k, int objective, const double *params, int n_p
         set_error("unknown objective id %d", objective);
         return VS_ERR_ARG;
     }
-    VS_TRY(ensure(c, c->obj_buf, h.size() * sizeof(double)));
-    VS_CUDA(cudaMemcpyAsync(c->obj_buf.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    VS_CUDA(cudaStreamSynchronize(c->stream));
+    if (!(c->obj_id_cached == objective && c->obj_host == h && c->obj_buf.p)) {
+        VS_CUDA(cudaStreamSynchronize(c->stream));   // a kernel in flight may still read the old parameters
+        c->obj_host = h;
+        VS_TRY(ensure(c, c->obj_buf, h.size() * sizeof(double)));
+        VS_CUDA(cudaMemcpyAsync(c->obj_buf.p, c->obj_host.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->obj_id_cached = objective;
+    }
     out->id = objective;
     out->params = (const double *)c->obj_buf.p;
     out->n_params = (int)h.size();
+    out->host = c->obj_host.data();
     return VS_OK;
 }
 

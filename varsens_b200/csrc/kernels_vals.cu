@@ -83,16 +83,12 @@ int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s
         return launch_eval_t(c, k, false, src, s, f, i_begin, i_end, fvals);
     }
     case VS_OBJ_ISHIGAMI: {
-        double h[2];
-        VS_CUDA(cudaMemcpyAsync(h, o.params, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        VS_CUDA(cudaStreamSynchronize(c->stream));
+        const double *h = o.host;
         Ishigami f{h[0], h[1]};
         return launch_eval_t(c, k, false, src, s, f, i_begin, i_end, fvals);
     }
     case VS_OBJ_RK4_CHAIN: {
-        double h[2];
-        VS_CUDA(cudaMemcpyAsync(h, o.params, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        VS_CUDA(cudaStreamSynchronize(c->stream));
+        const double *h = o.host;
         double dt = h[0];
         int ns = (int)h[1];
         switch (k / 2) {

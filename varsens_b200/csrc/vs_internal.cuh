@@ -57,6 +57,7 @@ struct ScaleDev {
     int kind;
     const double *lb;
     const double *wr;
+    const double *host;     // host copy: lb[k] | wr[k] (lives in the ctx)
 };
 
 // Where the unscaled points of the base design come from.
@@ -80,8 +81,9 @@ struct GramGeom {
 
 struct ObjectiveDev {
     int id;
-    const double *params;   // device copy of the host params (plus derived values, see functors.cuh)
+    const double *params;   // device copy of the host params (plus derived values, see device.cuh)
     int n_params;
+    const double *host;     // the same values on the host (lives in the ctx)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -112,6 +114,9 @@ struct vs_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     vs::HaltonCache halton;
+    // last uploaded descriptors: identical descriptors are not uploaded (or synchronised on) again
+    std::vector<double> scale_host, obj_host;
+    int scale_kind_cached = -1, scale_k_cached = -1, obj_id_cached = -1;
     // scratch
     vs::DevBuf scale_buf, obj_buf, perm_buf, raw_buf, io_buf, part_buf, block_buf, res_buf, dir_buf, misc_buf;
 };
