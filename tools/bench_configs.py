@@ -69,7 +69,7 @@ for label, gb in (("window_16GB", 16), ("window_64GB", 64), ("full_171GB", total
         continue
     buf = torch.empty((rows, k), dtype=torch.float64, device=dev)
     r0 = 0 if rows == total_rows else n + 12345                      # a window that straddles block boundaries
-    ms, _ = timeit(lambda: ctx.sample_flat(k, n, p, row_begin=r0, row_end=r0 + rows, out=buf), reps=3, warm=1)
+    ms, _ = timeit(lambda: ctx.sample_flat(k, n, p, row_begin=r0, row_end=r0 + rows, out=buf) is None, reps=3, warm=1)
     kms = ctx.last_kernel_ms()
     c4[label] = {"rows": rows, "bytes": need, "ms": ms, "kernel_ms": kms, "write_gbs": need / (kms * 1e-3) / 1e9,
                  "frac_of_hbm_peak": need / (kms * 1e-3) / 1e9 / HBM, "checksum": float(buf[::max(1, rows // 4096)].sum())}
@@ -79,7 +79,7 @@ for label, gb in (("window_16GB", 16), ("window_64GB", 64), ("full_171GB", total
 rows = int(16e9 / (k * 8))
 buf = torch.empty((rows, k), dtype=torch.float64, device=dev)
 sc = _cabi.Scale(_cabi.SCALE_LINEAR, numpy.linspace(-1, 0, k), numpy.linspace(1, 5, k))
-ms, _ = timeit(lambda: ctx.sample_flat(k, n, p, scale=sc, row_begin=0, row_end=rows, out=buf), reps=3, warm=1)
+ms, _ = timeit(lambda: ctx.sample_flat(k, n, p, scale=sc, row_begin=0, row_end=rows, out=buf) is None, reps=3, warm=1)
 c4["window_16GB_linear"] = {"bytes": rows * k * 8, "kernel_ms": ctx.last_kernel_ms(), "write_gbs": rows * k * 8 / (ctx.last_kernel_ms() * 1e-3) / 1e9}
 del buf
 torch.cuda.empty_cache()

@@ -193,7 +193,13 @@ class Context(object):
         check(lib().vs_ctx_synchronize(self._h))
 
     def set_stream(self, cuda_stream_ptr):
-        check(lib().vs_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+        """Run on a caller stream.  ``None`` = the ctx's own stream; ``0`` (torch's default stream handle) is mapped
+        to cudaStreamLegacy (0x1) so that torch events on the default stream really bracket the kernels."""
+        if cuda_stream_ptr is None:
+            ptr = 0
+        else:
+            ptr = int(cuda_stream_ptr) or 1
+        check(lib().vs_ctx_set_stream(self._h, ctypes.c_void_p(ptr)))
 
     def launch_count(self):
         return int(lib().vs_ctx_launch_count(self._h))

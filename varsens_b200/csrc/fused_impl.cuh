@@ -281,14 +281,12 @@ template <int K>
 __host__ __device__ constexpr int eval_groups() { return (2 + 2 * K + EG - 1) / EG; }
 
 template <int K, class F, int G, class YR>
-__device__ __forceinline__ void eval_group(const F &f, volatile double *tokp, const double (&a)[K], const double (&b)[K], bool valid,
+__device__ __forceinline__ void eval_group(const F &f, const double (&tk)[EG], const double (&a)[K], const double (&b)[K], bool valid,
                                            const YR &Yrow, double &fA, double &fB) {
     constexpr int M = 2 + 2 * K;
     constexpr int P0 = G * EG;
     constexpr int NP = (M - P0) < EG ? (M - P0) : EG;
-    double tk[NP], pr[NP];
-#pragma unroll
-    for (int u = 0; u < NP; ++u) tk[u] = *tokp;
+    double pr[NP];
     static_for<K>([&](auto Cc) {
         constexpr int C = decltype(Cc)::value;
         static_for<NP>([&](auto Uc) {
@@ -357,7 +355,27 @@ __device__ __forceinline__ void eval_rows(const F &f, volatile double *tokp, con
         // DFMA/DADD per step (FP64 latency covered inside one warp) and needs no k-long temporary arrays.
         fA = 0.0;
         fB = 0.0;
-        static_for<eval_groups<K>()>([&](auto Gc) { eval_group<K, F, decltype(Gc)::value>(f, tokp, a, b, valid, Yrow, fA, fB); });
+        // tokens of group g+1 are fetched before group g is evaluated: their LDS latency (long when other warps are
+        // hammering the table) is covered by a whole group of FP64 work
+        double tka[EG], tkb[EG];
+#pragma unroll
+        for (int u = 0; u < EG; ++u) tka[u] = *tokp;
+        static_for<eval_groups<K>()>([&](auto Gc) {
+            constexpr int GI = decltype(Gc)::value;
+            if constexpr (GI % 2 == 0) {
+                if constexpr (GI + 1 < eval_groups<K>()) {
+#pragma unroll
+                    for (int u = 0; u < EG; ++u) tkb[u] = *tokp;
+                }
+                eval_group<K, F, GI>(f, tka, a, b, valid, Yrow, fA, fB);
+            } else {
+                if constexpr (GI + 1 < eval_groups<K>()) {
+#pragma unroll
+                    for (int u = 0; u < EG; ++u) tka[u] = *tokp;
+                }
+                eval_group<K, F, GI>(f, tkb, a, b, valid, Yrow, fA, fB);
+            }
+        });
     } else {
         fA = f(a, *tokp);
         fB = f(b, *tokp);
@@ -771,8 +789,8 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     const uint64_t nbatch = (rows + 31) / 32;
     // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
     //   1 = single-role warps, register-tile Gram (also the first-order-only kernel)
-    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram (default)   6 = same with 3 E-warps per S-warp
-    int variant = SECOND ? 5 : 1;
+    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp (default)
+    int variant = SECOND ? 6 : 1;
     if (const char *ev = getenv("VS_FUSED_VARIANT")) variant = SECOND ? atoi(ev) : 1;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
