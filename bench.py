@@ -197,16 +197,14 @@ def run_gpu(args, rank, world):
 
     def step_resident():
         ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-        vdist.allreduce_partials(part)
-        return ctx.finalize(k, 1, n, part, flags)
+        return vdist.reduce_and_finalize(ctx, k, n, part, flags)     # NCCL all-reduce + finalize (VS_P2P=1: fused peer-memory kernel)
 
     def step_e2e():
         # public call with HOST buffers: permutation slice H2D from pinned memory, indices D2H, every step
         if world == 1:
             return ctx.run_fused(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, flags=flags)
         ctx.fused_partials(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-        vdist.allreduce_partials(part)
-        return ctx.finalize(k, 1, n, part, flags)
+        return vdist.reduce_and_finalize(ctx, k, n, part, flags)
 
     def barrier():
         if world > 1:
@@ -222,6 +220,9 @@ def run_gpu(args, rank, world):
         for _ in range(steps):
             flush.zero_()                                               # L2 flush between timed iterations
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()                                          # untimed: ranks enter the step together
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
@@ -268,7 +269,7 @@ def run_gpu(args, rank, world):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 Sobol g-function k=20 n=2^24 identity scaling, fused generic functor, second order on",
-                   "k": k, "n": n, "evals_per_step": evals(n), "parallelism": "rows sharded over %d rank(s), 1 all-reduce of %d doubles" % (world, plen),
+                   "k": k, "n": n, "evals_per_step": evals(n), "parallelism": "rows sharded over %d rank(s), 1 all-reduce of %d doubles (%s)" % (world, plen, "fused peer-memory kernel over NVLink" if (world > 1 and os.environ.get("VS_P2P", "0") == "1" and vdist.peer_exchange(plen, dev) is not None) else "NCCL" if world > 1 else "none"),
                    "l2": "192 MiB buffer written between timed iterations (L2 flush)", "index_time_ms": "included (finalize kernel + D2H of %d doubles)" % (6 * k + 2 + 2 * k * k)},
         "e2e": {"value": evals(n) / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k))},

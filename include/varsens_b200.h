@@ -138,6 +138,16 @@ int vs_partials_from_values(vs_ctx *ctx, int k, int l, uint64_t rows, const doub
  * unbiased variance of the 2*rows surviving values while E_2 and U keep dividing by n and n-1). */
 int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *partials, int partials_mem,
                 int flags, vs_result *result);
+/* Multi-GPU: vs_finalize fused with the all-reduce, over NVLink peer memory (no NCCL call).  ONE single-CTA kernel per
+ * rank: stores this rank's partial sums into slot `rank` of every peer's exchange buffer (peer_bufs[r], device pointers
+ * mapped into this process, e.g. torch symmetric memory), publishes an epoch flag to every peer (peer_flags[r][rank]),
+ * waits for the world_size flags in its own flag array, sums the slots in rank order (identical bits on every rank) and
+ * computes the indices.  Each peer buffer holds 2 * world_size * vs_partials_len(k,l) doubles and each flag array
+ * 2 * world_size uint32 (double-buffered on the epoch parity; zero-initialised).  epoch must start at 1 and increase by one
+ * per call on every rank.  Replaces the file-batch gather of varsens/saltelli.py:415-472 + :572-622. */
+int vs_allreduce_finalize_p2p(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, int world_size, int rank,
+                              const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch,
+                              const double *partials_dev, int flags, vs_result *result);
 /* vs_partials_from_values + vs_finalize over a whole design (Objective(objective_vals=...) route,
  * varsens/saltelli.py:297-298 -> :572-622).  rows may be < n after NaN trimming (:474-495). */
 int vs_indices_from_values(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *fvals,

@@ -23,7 +23,7 @@ SYMBOLS = (
     "vs_abi_version", "vs_last_error", "vs_ctx_create", "vs_ctx_destroy", "vs_ctx_set_stream",
     "vs_ctx_synchronize", "vs_ctx_launch_count", "vs_halton_bases", "vs_halton_terms", "vs_partials_len",
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
-    "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
+    "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
 )
 
 
@@ -75,6 +75,7 @@ def lib():
         L.vs_eval_values.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, vp, i32]
         L.vs_partials_from_values.argtypes = [vp, i32, i32, u64, vp, i32, vp, i32, vp, i32]
         L.vs_finalize.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
+        L.vs_allreduce_finalize_p2p.argtypes = [vp, i32, i32, u64, u64, i32, i32, vp, vp, ctypes.c_uint32, vp, i32, P(vs_result)]
         L.vs_indices_from_values.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
         L.vs_fused_partials.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32,
                                         vp, i32]
@@ -275,6 +276,20 @@ class Context(object):
         pp, pm, pk = buf(partials, numpy.float64)
         check(lib().vs_finalize(self._h, int(k), int(l), int(n), int(n if rows is None else rows), pp, pm, int(flags),
                                 ctypes.byref(cs)))
+        return res
+
+    def allreduce_finalize_p2p(self, k, l, n, world_size, rank, peer_bufs, peer_flags, epoch, partials, flags=FLAG_SECOND_ORDER,
+                               rows=None):
+        """All-reduce over NVLink peer memory fused with the finalisation (vs_allreduce_finalize_p2p)."""
+        res = Result(k, l, bool(flags & FLAG_SECOND_ORDER))
+        cs = res.c_struct()
+        pb = (ctypes.c_uint64 * world_size)(*[int(x) for x in peer_bufs])
+        pf = (ctypes.c_uint64 * world_size)(*[int(x) for x in peer_flags])
+        pp, pm, pk = buf(partials, numpy.float64)
+        if pm != MEM_DEVICE:
+            raise VarsensError("partials must be a device tensor")
+        check(lib().vs_allreduce_finalize_p2p(self._h, int(k), int(l), int(n), int(n if rows is None else rows), int(world_size),
+                                              int(rank), pb, pf, int(epoch), pp, int(flags), ctypes.byref(cs)))
         return res
 
     def indices_from_values(self, k, l, n, rows, fvals, flags=FLAG_SECOND_ORDER):

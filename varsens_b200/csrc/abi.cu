@@ -182,6 +182,25 @@ extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, c
     return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
 }
 
+extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world_size, int rank,
+                                         const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch,
+                                         const double *partials_dev, int flags, vs_result *result) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result, VS_ERR_ARG, "bad arguments");
+    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && peer_flags && epoch >= 1,
+               VS_ERR_ARG, "bad peer description");
+    VS_REQUIRE(partials_dev != c->part_buf.p, VS_ERR_ARG, "partials_dev must be a caller buffer");
+    // the two pointer tables travel as kernel-visible device arrays (dir_buf: world_size * 2 pointers)
+    VS_TRY(ensure(c, c->dir_buf, 2 * 64 * sizeof(uint64_t)));
+    uint64_t *tab = (uint64_t *)c->dir_buf.p;
+    VS_CUDA(cudaMemcpyAsync(tab, peer_bufs, world_size * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    VS_CUDA(cudaMemcpyAsync(tab + 64, peer_flags, world_size * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
+    VS_TRY(launch_p2p_reduce_finalize(c, k, l, n, rows, world_size, rank, tab, tab + 64, epoch, partials_dev, flags,
+                                      (double *)c->res_buf.p));
+    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+}
+
 extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *fvals, int fvals_mem,
                                       int flags, vs_result *result) {
     VS_TRY(check_common(c, k));

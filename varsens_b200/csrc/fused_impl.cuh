@@ -743,35 +743,52 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 }
 
 // CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector, CTA order.
+// Sum of one entry over all CTA partials, in CTA order (bit-reproducible); the loads of 8 CTAs are issued together so the
+// ~150 L2 round trips of a thread overlap instead of queueing behind each other.
+__device__ __forceinline__ double sum_over_blocks(const double *__restrict__ p, size_t stride, int nblocks) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 8 <= nblocks; b += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(b + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < nblocks; ++b) s += p[(size_t)b * stride];
+    return s;
+}
+
+// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector, CTA order.
 static __global__ void __launch_bounds__(256) dense_scatter_kernel(int m, int mpad, int nblocks, const double *__restrict__ blockpart,
-                                                            double *__restrict__ partials) {
+                                                                   double *__restrict__ partials) {
     const size_t per_block = (size_t)mpad * mpad + 4;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < 4) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + (size_t)mpad * mpad + e];
-        partials[e] = s;
-    }
+    if (e < 4) partials[e] = sum_over_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
     if (e >= mpad * mpad) return;
     const int p = e / mpad, q = e % mpad;
     if (p >= m || q >= m || p > q) return;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + e];
-    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = s;
+    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = sum_over_blocks(blockpart + e, per_block, nblocks);
 }
 
 // f(M_1[0]): the common shift for the variance sums (identical on every rank).
 template <int K, class F>
 __global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double x[K];
-    for (int d = 0; d < K; ++d) {
+    __shared__ double xs[K];
+    const int d = threadIdx.x;                     // one thread per coordinate: the table reads of the 20 chains overlap
+    if (d < K) {
         double p = src.raw ? src.raw[d] : halton_coord(src.h, d, (uint32_t)src.start);
         if (fc.scale_kind == VS_SCALE_LINEAR) p = __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);
         else if (fc.scale_kind == VS_SCALE_POWER) p = __dmul_rn(fc.lb[d], pow(fc.wr[d], p));
-        x[d] = p;
+        xs[d] = p;
     }
-    *out = f(x, F::token);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) x[c] = xs[c];
+        *out = f(x, F::token);
+    }
 }
 
 template <int K, class F, bool SECOND, bool SEPARABLE>
@@ -802,7 +819,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             const size_t per_block = (size_t)MPADk * MPADk + 4;
             VS_TRY(ensure(c, c->block_buf, (size_t)gridd * per_block * sizeof(double)));
             VS_TRY(ensure(c, c->misc_buf, 64));
-            shift_kernel<K, F><<<1, 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
+            shift_kernel<K, F><<<1, (K + 31) / 32 * 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
             c->launches++;
             size_t smem_run = ((size_t)nterms + 1 + 2 * eps * WS_S + (size_t)eps * WS_S * MPADk * YT_PITCH) * sizeof(double);
             size_t smem_red = ((size_t)WS_S * MPADk * MPADk + 4 * eps * WS_S) * sizeof(double);
@@ -844,7 +861,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     if (grid < 1) grid = 1;
     VS_TRY(ensure(c, c->block_buf, (size_t)grid * PER_BLOCK * sizeof(double)));
     VS_TRY(ensure(c, c->misc_buf, 64));
-    shift_kernel<K, F><<<1, 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
+    shift_kernel<K, F><<<1, (K + 31) / 32 * 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
     c->launches++;
     {
         size_t smem_run = ((size_t)nterms + 1 + (size_t)FUSED_WARPS * 32 * MP) * sizeof(double);

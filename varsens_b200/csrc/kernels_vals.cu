@@ -210,7 +210,15 @@ __global__ void __launch_bounds__(256) gram_scatter_kernel(GramGeom g, int nbloc
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     for (size_t e = gid; e < per_block; e += nthreads) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + e];
+        int b = 0;
+        for (; b + 8 <= nblocks; b += 8) {               // 8 loads in flight, added in CTA order (bit-reproducible)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = blockpart[(size_t)(b + u) * per_block + e];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < nblocks; ++b) s += blockpart[(size_t)b * per_block + e];
         if (e >= tile_elems) {
             partials[e - tile_elems] = s;
             continue;
@@ -321,8 +329,8 @@ __device__ __forceinline__ double gram_at(const double *G, int m, int p, int q) 
     return G[(size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)];
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
-                                                       double *__restrict__ res) {
+__device__ void finalize_body(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
+                              double *__restrict__ res) {
     const int m = (2 + 2 * k) * l;
     const double *G = P + 4 * l;
     const int kl = k * l;
@@ -370,6 +378,59 @@ __global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, d
         s2[e] = v2;
         s2n[e] = v2n;
     }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
+                                                       double *__restrict__ res) {
+    finalize_body(k, l, n, rows, P, second_order, res);
+}
+
+// Partial-sum all-reduce over NVLink peer memory fused with the finalisation (see vs_allreduce_finalize_p2p).
+// Single CTA.  bufs[r] / flgs[r] are rank r's exchange buffer / flag array as mapped into this process.
+__global__ void __launch_bounds__(256) p2p_reduce_finalize_kernel(int k, int l, double n, double rows, int world, int rank,
+                                                                  const uint64_t *__restrict__ bufs, const uint64_t *__restrict__ flgs,
+                                                                  unsigned epoch, int plen, const double *__restrict__ mine,
+                                                                  int second_order, double *__restrict__ reduced, double *__restrict__ res) {
+    const int set = (int)(epoch & 1u);
+    // 1. my partial sums -> slot `rank` of every rank's buffer (remote stores over NVLink; the local one is a plain store)
+    for (int r = 0; r < world; ++r) {
+        double *dst = reinterpret_cast<double *>(bufs[r]) + ((size_t)set * world + rank) * plen;
+        for (int e = threadIdx.x; e < plen; e += blockDim.x) dst[e] = mine[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish: flag[set][rank] = epoch on every rank; then wait for everybody's flag in my own array
+    if (threadIdx.x < world) {
+        volatile unsigned *f = reinterpret_cast<volatile unsigned *>(flgs[threadIdx.x]) + (size_t)set * world + rank;
+        *f = epoch;
+    }
+    if (threadIdx.x < world) {
+        volatile unsigned *f = reinterpret_cast<volatile unsigned *>(flgs[rank]) + (size_t)set * world + threadIdx.x;
+        while (*f != epoch) __nanosleep(100);
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 3. sum the slots in rank order (same order, hence same bits, on every rank)
+    const double *slots = reinterpret_cast<const double *>(bufs[rank]) + (size_t)set * world * plen;
+    for (int e = threadIdx.x; e < plen; e += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += __ldcv(slots + (size_t)r * plen + e);
+        reduced[e] = s;
+    }
+    __syncthreads();
+    finalize_body(k, l, n, rows, reduced, second_order, res);
+}
+
+int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world, int rank, const uint64_t *peer_bufs_dev,
+                               const uint64_t *peer_flags_dev, uint32_t epoch, const double *partials, int flags, double *res_dev) {
+    const int plen = (int)vs_partials_len(k, l);
+    VS_TRY(ensure(c, c->part_buf, (size_t)plen * sizeof(double)));
+    p2p_reduce_finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, (double)rows, world, rank, peer_bufs_dev, peer_flags_dev, epoch,
+                                                          plen, partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0,
+                                                          (double *)c->part_buf.p, res_dev);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
 }
 
 int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials, int flags, double *res_dev) {

@@ -147,6 +147,8 @@ int launch_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const do
                                 int flags, double *partials);
 int launch_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials, int flags, double *res_dev);
 size_t result_len(int k, int l);
+int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world, int rank, const uint64_t *peer_bufs_dev,
+                               const uint64_t *peer_flags_dev, uint32_t epoch, const double *partials, int flags, double *res_dev);
 int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
 // kernels_fused.cu
 bool fused_supported(int k, int objective, int flags);
