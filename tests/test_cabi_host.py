@@ -153,3 +153,15 @@ def test_two_rank_allreduce_over_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK" in outs[0]
+
+
+def test_fast_digit_step_is_exact():
+    """The multiply-only quotient/remainder step of the fused kernels (csrc/fused_impl.cuh digit_step) -- brute force."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_fastdiv.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+
+
+def test_sobol_direction_numbers_match_oracle():
+    from varsens_b200 import sobol as vsobol
+    from oracle import sobol as osobol
+    assert (vsobol.joe_kuo_direction_numbers(40) == osobol.joe_kuo_direction_numbers(40)).all()

@@ -98,6 +98,24 @@ def test_sobol_skip_ahead(ctx, golden):
     assert (q == osobol.quantize_6sig(osobol.sobol_points(V50[:3], 1, 70000))).all()
 
 
+def test_sobol_sample_entry(vb, golden):
+    """quantlib/sobolGen.cpp -> CSV -> Sample(loadFile=...) replaced by sobol_raw -> Sample(raw=...)."""
+    k, n = 8, 16
+    raw = vb.sobol_raw(k, n)                                              # 6-digit quantised, first point 4097
+    assert raw.shape == (2 * n, k)
+    assert (raw == osobol.quantize_6sig(golden["sobol_joekuo_k8_from4097"])).all()
+    assert (vb.sobol_raw(k, n, quantize6=False) == golden["sobol_joekuo_k8_from4097"]).all()
+    assert (vb.joe_kuo_direction_numbers(8) == golden["sobol_joekuo_k8_dirnums"]).all()
+    lb, ub = numpy.linspace(-1, 0, k), numpy.linspace(1, 9, k)
+    s = vb.Sample(k, n, lambda x: vb.scale.linear(x, lb, ub), verbose=False, raw=raw)
+    o = osalt.Sample(k, n, lambda x: oscale.linear(x, lb, ub), verbose=False, raw=raw.copy())
+    assert (s.flat() == o.flat()).all()
+    v = vb.Varsens(vb.GFunction(numpy.linspace(0, 9, k)), sample=vb.Sample(k, n, verbose=False, raw=raw), verbose=False)
+    ref = cport.run(k, n, cport.OBJ_GFUNCTION, numpy.linspace(0, 9, k), raw=raw)
+    close(v.sens, ref["sens"])
+    close(v.sens_2, ref["sens_2"])
+
+
 # ------------------------------------------------------------------------------------------------
 # K3 sample assembly / export mode
 # ------------------------------------------------------------------------------------------------
