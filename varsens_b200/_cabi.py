@@ -10,7 +10,7 @@ import threading
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvarsens_b200.so")
+LIB_PATH = os.environ.get("VS_LIB") or os.path.join(_HERE, "libvarsens_b200.so")   # VS_LIB: alternative builds (kernel experiments)
 
 VS_OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
