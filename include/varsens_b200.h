@@ -138,6 +138,11 @@ int vs_partials_from_values(vs_ctx *ctx, int k, int l, uint64_t rows, const doub
  * unbiased variance of the 2*rows surviving values while E_2 and U keep dividing by n and n-1). */
 int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *partials, int partials_mem,
                 int flags, vs_result *result);
+/* vs_finalize without the device-to-host copy: the 2l + 4kl + 2(kl)^2 result doubles (E_2, var_y, U_j, U_nj, sens, sens_t,
+ * sens_2, sens_2n, in that order) are left in the caller's device buffer and nothing is synchronised -- the form to
+ * capture in a CUDA graph together with vs_fused_partials (device buffers) and the all-reduce. */
+int vs_finalize_device(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *partials_dev, int flags,
+                       double *result_dev);
 /* Multi-GPU: vs_finalize fused with the all-reduce, over NVLink peer memory (no NCCL call).  ONE single-CTA kernel per
  * rank: stores this rank's partial sums into slot `rank` of every peer's exchange buffer (peer_bufs[r], device pointers
  * mapped into this process, e.g. torch symmetric memory), publishes an epoch flag to every peer (peer_flags[r][rank]),

@@ -23,7 +23,7 @@ SYMBOLS = (
     "vs_abi_version", "vs_last_error", "vs_ctx_create", "vs_ctx_destroy", "vs_ctx_set_stream",
     "vs_ctx_synchronize", "vs_ctx_launch_count", "vs_halton_bases", "vs_halton_terms", "vs_partials_len",
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
-    "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
+    "vs_finalize_device", "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
 )
 
 
@@ -75,6 +75,7 @@ def lib():
         L.vs_eval_values.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, vp, i32]
         L.vs_partials_from_values.argtypes = [vp, i32, i32, u64, vp, i32, vp, i32, vp, i32]
         L.vs_finalize.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
+        L.vs_finalize_device.argtypes = [vp, i32, i32, u64, u64, vp, i32, vp]
         L.vs_allreduce_finalize_p2p.argtypes = [vp, i32, i32, u64, u64, i32, i32, vp, vp, ctypes.c_uint32, vp, i32, P(vs_result)]
         L.vs_indices_from_values.argtypes = [vp, i32, i32, u64, u64, vp, i32, i32, P(vs_result)]
         L.vs_fused_partials.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32,
@@ -155,6 +156,24 @@ class Result(object):
         self.sens_t = numpy.zeros((k, l))
         self.sens_2 = numpy.zeros((k, l, k, l)) if second_order else None
         self.sens_2n = numpy.zeros((k, l, k, l)) if second_order else None
+
+    @staticmethod
+    def flat_len(k, l):
+        return 2 * l + 4 * k * l + 2 * (k * l) ** 2
+
+    @classmethod
+    def from_flat(cls, k, l, flat, second_order=True):
+        """Unpack the device result layout of vs_finalize_device (a host numpy copy of it)."""
+        r = cls(k, l, second_order)
+        kl, at = k * l, 0
+        for name, cnt, shape in (("E_2", l, (l,)), ("var_y", l, (l,)), ("U_j", kl, (k, l)), ("U_nj", kl, (k, l)),
+                                 ("sens", kl, (k, l)), ("sens_t", kl, (k, l)), ("sens_2", kl * kl, (k, l, k, l)),
+                                 ("sens_2n", kl * kl, (k, l, k, l))):
+            if name.startswith("sens_2") and not second_order:
+                break
+            setattr(r, name, numpy.array(flat[at:at + cnt], dtype=numpy.float64).reshape(shape))
+            at += cnt
+        return r
 
     def c_struct(self):
         def p(a):
@@ -277,6 +296,15 @@ class Context(object):
         check(lib().vs_finalize(self._h, int(k), int(l), int(n), int(n if rows is None else rows), pp, pm, int(flags),
                                 ctypes.byref(cs)))
         return res
+
+    def finalize_device(self, k, l, n, partials, out, flags=FLAG_SECOND_ORDER, rows=None):
+        """vs_finalize_device: results stay in the CUDA tensor `out` (Result.from_flat unpacks a host copy); nothing syncs."""
+        pp, pm, pk = buf(partials, numpy.float64)
+        op, om, ok_ = buf(out, numpy.float64)
+        if pm != MEM_DEVICE or om != MEM_DEVICE:
+            raise VarsensError("finalize_device needs device tensors")
+        check(lib().vs_finalize_device(self._h, int(k), int(l), int(n), int(n if rows is None else rows), pp, int(flags), op))
+        return out
 
     def allreduce_finalize_p2p(self, k, l, n, world_size, rank, peer_bufs, peer_flags, epoch, partials, flags=FLAG_SECOND_ORDER,
                                rows=None):

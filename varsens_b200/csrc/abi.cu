@@ -182,6 +182,13 @@ extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, c
     return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
 }
 
+extern "C" int vs_finalize_device(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials_dev, int flags,
+                                  double *result_dev) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    VS_REQUIRE(k >= 1 && l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result_dev, VS_ERR_ARG, "bad arguments");
+    return launch_finalize(c, k, l, n, rows, partials_dev, flags, result_dev);
+}
+
 extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world_size, int rank,
                                          const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch,
                                          const double *partials_dev, int flags, vs_result *result) {
@@ -191,10 +198,14 @@ extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, ui
                VS_ERR_ARG, "bad peer description");
     VS_REQUIRE(partials_dev != c->part_buf.p, VS_ERR_ARG, "partials_dev must be a caller buffer");
     // the two pointer tables travel as kernel-visible device arrays (dir_buf: world_size * 2 pointers)
-    VS_TRY(ensure(c, c->dir_buf, 2 * 64 * sizeof(uint64_t)));
-    uint64_t *tab = (uint64_t *)c->dir_buf.p;
-    VS_CUDA(cudaMemcpyAsync(tab, peer_bufs, world_size * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    VS_CUDA(cudaMemcpyAsync(tab + 64, peer_flags, world_size * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    VS_TRY(ensure(c, c->peer_buf, 2 * 64 * sizeof(uint64_t)));
+    uint64_t *tab = (uint64_t *)c->peer_buf.p;
+    std::vector<uint64_t> want(128, 0);
+    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags[r]; }
+    if (want != c->peer_tab) {                              // uploaded once per exchange, not per call
+        c->peer_tab = want;
+        VS_CUDA(cudaMemcpyAsync(tab, c->peer_tab.data(), 128 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    }
     VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
     VS_TRY(launch_p2p_reduce_finalize(c, k, l, n, rows, world_size, rank, tab, tab + 64, epoch, partials_dev, flags,
                                       (double *)c->res_buf.p));

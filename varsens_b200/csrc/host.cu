@@ -53,10 +53,17 @@ int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, c
     return VS_OK;
 }
 
+static bool capturing(vs_ctx *c) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c->stream, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
 void time_begin(vs_ctx *c) {
+    if (capturing(c)) return;                     // events recorded inside a CUDA graph capture cannot be timed
     cudaEventRecord(c->ev0, c->stream);
 }
 void time_end(vs_ctx *c) {
+    if (capturing(c)) return;
     cudaEventRecord(c->ev1, c->stream);
     c->timed = true;
 }
@@ -286,7 +293,7 @@ extern "C" int vs_ctx_destroy(vs_ctx *c) {
     if (!c) return VS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
+    DevBuf *bufs[] = {&c->peer_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
                       &c->part_buf,  &c->block_buf, &c->res_buf, &c->dir_buf, &c->misc_buf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);

@@ -116,6 +116,8 @@ struct vs_ctx {
     vs::HaltonCache halton;
     // last uploaded descriptors: identical descriptors are not uploaded (or synchronised on) again
     std::vector<double> scale_host, obj_host;
+    std::vector<uint64_t> peer_tab;
+    vs::DevBuf peer_buf;
     int scale_kind_cached = -1, scale_k_cached = -1, obj_id_cached = -1;
     // scratch
     vs::DevBuf scale_buf, obj_buf, perm_buf, raw_buf, io_buf, part_buf, block_buf, res_buf, dir_buf, misc_buf;
