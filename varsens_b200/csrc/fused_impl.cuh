@@ -45,7 +45,8 @@ struct FusedConst {            // kernel parameter -> constant bank; indexed wit
     uint32_t nd[K];            // digits to sum for the largest index of the run
     uint32_t ndc[K];           // digit rows the cached global table holds per dimension (layout: toff)
     int small_index;           // every Halton index of the run is < 2^29
-    int alternate;             // E-warp teams alternate generate / evaluate phases (see fused_wsd_kernel)
+    int alternate;             // (EPS == 2) E-warp teams alternate generate / evaluate phases -- measured slower, off
+    int rotate;                // (EPS == 3) rotating generate / evaluate / evaluate schedule (see fused_wsd_kernel)
     long long *trace;          // profiling only (VS_TRACE): per-warp clock stamps of CTA 0, else nullptr
     int scale_kind;
     int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
@@ -612,13 +613,80 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         // a warp that generates while the others evaluate finds the LSU free, finishes early and catches up -- and
         // then the two phases add up (clock stamps: 12.6k + 10.5k cycles per batch).  A named barrier over the E-warps
         // after every phase pins team 0 to "generate" while team 1 "evaluates" and vice versa.
+        // ---- rotating schedule (EPS == 3, product-form generic path; fc.rotate) --------------------------------------
+        // The three E-warps of a sub-partition are pinned to three different phases by a named barrier after every slot:
+        //   team (s mod 3)   : GENERATE its next batch        (integer + shared-memory pipe, 4 warps per SM at a time)
+        //   the other two    : first / second half of their EVALUATION (two warps share the FP64 pipe and hide its latency)
+        // so one batch per sub-partition completes per slot and generation always runs under evaluation.  Without the
+        // barrier the warps drift into lock-step (all generate, then all evaluate) and the two phases add up.
+        bool rotated = false;
+        if constexpr (EPS == 3 && F::separable && !SEPARABLE) {
+            if (fc.rotate && fc.debug == 0) {
+                rotated = true;
+                auto rbar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
+                const int team = e / WS_S;
+                const uint64_t nslots = 3 * count_of(0) + 2;            // count_of(0) is the largest batch count in the CTA
+                constexpr int NE = eval_groups<K>(), NE1 = (NE + 1) / 2;
+                double a[K], b[K];
+                bool valid = false;
+                double fA = 0.0, fB = 0.0;
+                uint64_t it = 0;
+                for (uint64_t sl = 0; sl < nslots; ++sl) {
+                    const int q = (int)((sl + 3 - team) % 3);
+                    if (sl >= (uint64_t)team && it < cnt) {
+                        const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 64;
+                        long long *trp = fc.trace + ((size_t)warp * 64 + (it < 64 ? it : 0)) * 4;
+                        const YRef Yrow{tiles + (size_t)e * TILE + lane, YT_PITCH};
+                        if (q == 0) {
+                            if (tr_on) trp[0] = clock64();
+                            valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+                                a[d] = xa;
+                                b[d] = xb;
+                            });
+                            if (tr_on) trp[1] = clock64();
+                        } else if (q == 1) {
+                            mbar_wait(empty_bar(e, 0), (uint32_t)((it & 1) ^ 1));
+                            if (tr_on) trp[2] = clock64();
+                            static_for<NE1>([&](auto Gc) {
+                                double tk[EG];
+#pragma unroll
+                                for (int u = 0; u < EG; ++u) tk[u] = *tokp;
+                                eval_group<K, F, decltype(Gc)::value>(f, tk, a, b, valid, Yrow, fA, fB);
+                            });
+                        } else {
+                            static_for<NE - NE1>([&](auto Gc) {
+                                double tk[EG];
+#pragma unroll
+                                for (int u = 0; u < EG; ++u) tk[u] = *tokp;
+                                eval_group<K, F, NE1 + decltype(Gc)::value>(f, tk, a, b, valid, Yrow, fA, fB);
+                            });
+                            Yrow[0] = valid ? fA : 0.0;
+                            Yrow[1] = valid ? fB : 0.0;
+                            if (valid) {
+                                double dA = fA - shift, dB = fB - shift;
+                                sA += dA;
+                                qA = fma(dA, dA, qA);
+                                sB += dB;
+                                qB = fma(dB, dB, qB);
+                            }
+                            __syncwarp();
+                            if (tr_on) trp[3] = clock64();
+                            if (lane == 0) mbar_arrive(full_bar(e, 0));
+                            ++it;
+                            bt += G;
+                        }
+                    }
+                    rbar();
+                }
+            }
+        }
         const bool alternate = (EPS == 2) && fc.alternate;
         auto ebar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
         const int team = e / WS_S;
         const uint64_t bars_total = 2 * count_of(0) + 1;              // count_of(0) is the largest batch count in the CTA
         uint64_t bars_done = 0;
         if (alternate && team == 1) { ebar(); ++bars_done; }
-        for (uint64_t it = 0; it < cnt; ++it, bt += G) {
+        for (uint64_t it = 0; !rotated && it < cnt; ++it, bt += G) {
             const int slot = (int)(it % NBUF);
             double a[K], b[K];
             bool valid = bt * 32 + lane < rows;
@@ -893,6 +961,7 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
     fc.small_index = 0;
     fc.trace = nullptr;
     fc.alternate = getenv("VS_ALTERNATE") ? atoi(getenv("VS_ALTERNATE")) : 0;
+    fc.rotate = getenv("VS_ROTATE") ? atoi(getenv("VS_ROTATE")) : 0;
     if (getenv("VS_TRACE")) {
         VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
         VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));

@@ -145,11 +145,27 @@ __global__ void __launch_bounds__(256) gram_kernel(GramGeom g, uint64_t rows, co
         // stage: global element (t, r, o) at fvals[(t*rows + r0 + r)*l + o] -> Y[r][t*l + o]
         const int per_t = g.R * g.l;
         const int nT = g.m / g.l;
-        for (int e = tid; e < nT * per_t; e += blockDim.x) {
-            int t = e / per_t, rem = e - t * per_t;
-            int r = rem / g.l, o = rem - r * g.l;
-            double v = (r < valid) ? fvals[((uint64_t)t * rows + r0 + r) * g.l + o] : 0.0;
-            Y[r * g.mp + t * g.l + o] = v;
+        // Loads first (4 independent requests in flight per thread), then the transposed stores: with one load per loop
+        // trip the kernel sat on HBM latency (2.0 ms for 1.4 GB; this form: see profiles/r01_other_configs.json).
+        const int total = nT * per_t;
+        for (int e0 = tid; e0 < total; e0 += 4 * (int)blockDim.x) {
+            double v[4];
+            int dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * (int)blockDim.x;
+                dst[u] = -1;
+                v[u] = 0.0;
+                if (e < total) {
+                    int t = e / per_t, rem = e - t * per_t;
+                    int r = rem / g.l, o = rem - r * g.l;
+                    dst[u] = r * g.mp + t * g.l + o;
+                    if (r < valid) v[u] = __ldg(fvals + ((uint64_t)t * rows + r0 + r) * g.l + o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dst[u] >= 0) Y[dst[u]] = v[u];
         }
         for (int e = tid; e < g.R * (g.mp - g.m); e += blockDim.x) {   // zero the column padding
             int r = e / (g.mp - g.m), cidx = g.m + e % (g.mp - g.m);
@@ -277,7 +293,11 @@ static int launch_gram_t(vs_ctx *c, const GramGeom &g, uint64_t rows, const doub
     VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "Gram tile needs %zu bytes of shared memory", smem);
     VS_CUDA(cudaFuncSetAttribute(gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t nchunks = (rows + g.R - 1) / g.R;
-    int gx = (int)(nchunks < (uint64_t)(2 * c->sm_count) ? nchunks : (uint64_t)(2 * c->sm_count));
+    // as many CTAs per SM as shared memory allows (up to 8): the staging loads need memory-level parallelism
+    int per_sm = (int)((c->smem_optin > 0 ? (size_t)200 * 1024 : (size_t)48 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int gx = (int)(nchunks < (uint64_t)(per_sm * c->sm_count) ? nchunks : (uint64_t)(per_sm * c->sm_count));
     if (gx < 1) gx = 1;
     size_t per_block = (size_t)g.passes * g.LG * (T * T) + 4 * (size_t)g.l;
     VS_TRY(ensure(c, c->block_buf, (size_t)gx * per_block * sizeof(double)));
