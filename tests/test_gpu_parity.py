@@ -190,7 +190,8 @@ def test_sample_flat_large_property(ctx):
 # estimators on given values
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,n,l", [(1, 2, 1), (3, 50, 1), (6, 1024, 1), (6, 256, 2), (20, 4096, 1), (50, 600, 1),
-                                   (10, 333, 3), (100, 70, 1)])
+                                   (10, 333, 3), (100, 70, 1), (20, 4098, 1), (23, 66, 1), (24, 1000, 1), (31, 130, 1),
+                                   (50, 1026, 1), (7, 333, 1), (100, 130, 1), (150, 64, 1)])
 def test_indices_from_values(ctx, k, n, l):
     rng = numpy.random.RandomState(k * 1000 + n + l)
     vals = rng.rand(2 * n * (1 + k), l) * 3.0 + 10.0
@@ -208,6 +209,40 @@ def test_indices_from_values_reference_goldens(ctx, refgold):
     res = ctx.indices_from_values(6, 2, 256, 256, refgold["two_obj_flat"])
     for name in NAMES:
         close(getattr(res, name), refgold["two_" + name].reshape(getattr(res, name).shape))
+
+
+@pytest.mark.parametrize("k,rows", [(3, 70), (20, 1030), (28, 514), (50, 258), (100, 66)])
+def test_partials_tensor_path_matches_register_path(ctx, k, rows, monkeypatch):
+    """l = 1 with an even row count runs the bulk-copy + DMMA kernel; VS_GRAM_MMA=0 forces the register-tile kernel.
+    Both must give the same sufficient statistics (different summation order -> tolerance), with and without the
+    second-order block, and the tensor path must be bit-reproducible."""
+    rng = numpy.random.RandomState(k + rows)
+    vals = rng.rand(2 + 2 * k, rows) * 2.0 + 5.0
+    for flags in (vb_flags_second(), 0):
+        monkeypatch.delenv("VS_GRAM_MMA", raising=False)
+        a = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
+        a2 = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
+        assert (a == a2).all()
+        monkeypatch.setenv("VS_GRAM_MMA", "0")
+        b = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
+        m = 2 + 2 * k
+        # compare what the estimators read: sums + Gram rows 0,1 (first order) or the whole upper triangle
+        want = vals @ vals.T
+        G = numpy.zeros((m, m))
+        G[numpy.triu_indices(m)] = a[4:]
+        Gb = numpy.zeros((m, m))
+        Gb[numpy.triu_indices(m)] = b[4:]
+        top = m if flags else 2
+        numpy.testing.assert_allclose(G[:top], numpy.triu(want)[:top], rtol=1e-13)
+        numpy.testing.assert_allclose(G[:top], Gb[:top], rtol=1e-13)
+        numpy.testing.assert_allclose(a[:4], b[:4], rtol=1e-11, atol=1e-9)
+        d = vals[:2] - vals[0, 0]
+        numpy.testing.assert_allclose(a[:4], [d[0].sum(), d[1].sum(), (d[0] ** 2).sum(), (d[1] ** 2).sum()], rtol=1e-11, atol=1e-9)
+
+
+def vb_flags_second():
+    from varsens_b200 import _cabi
+    return _cabi.FLAG_SECOND_ORDER
 
 
 def test_partials_shards_sum_to_whole(ctx):

@@ -1,0 +1,12 @@
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from varsens_b200 import Context
+ctx = Context(0)
+k, rows = int(sys.argv[1]), 1 << int(sys.argv[2])
+m = 2 + 2 * k
+vals = torch.rand(m * rows, dtype=torch.float64, device="cuda") + 1.0
+out = torch.empty(4 + m * (m + 1) // 2, dtype=torch.float64, device="cuda")
+for _ in range(2):
+    ctx.partials_from_values(k, 1, rows, vals, shift=[1.5], out=out)
+ctx.synchronize()
+print("ms", ctx.last_kernel_ms())

@@ -1,0 +1,460 @@
+// Estimator reductions on given values, tensor path (scalar objectives, l = 1).
+//
+// Computes the same partial-sum vector as gram_kernel (kernels_vals.cu) -- the symmetric Gram
+// G = sum_i v_i v_i^T of the per-row vector v_i = (f(M_1[i]), f(M_2[i]), f(N_j[.][i]), f(N_nj[.][i])) plus the
+// shifted sums for var_y, i.e. everything varsens/saltelli.py:577-622 reads -- but shaped for the hardware:
+//
+//   * the value layout handed over by the reference API is column-major already (flat() order: all rows of M_1,
+//     then M_2, ... -> fvals[t * rows + r]), so a chunk of RC rows is m contiguous runs of RC doubles.  One producer
+//     warp moves them with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) into a ring of shared-memory
+//     stages Yt[p][RC + 4]; nothing is transposed and no thread waits on a global load.
+//   * consumer warps run the Gram update on the FP64 tensor path (mma.sync m8n8k4): the fragment
+//     Yt[8P + lane/4][r0 + lane%4] is both the A and the B operand of G[P][Q] += Y[r0..r0+4, P]^T Y[r0..r0+4, Q]
+//     and loads conflict-free (pitch = 4 mod 16).  A warp owns one ST x ST super-tile of 8x8 blocks (its accumulators
+//     never leave registers) and a subset of the 4-row steps of every chunk.
+//   * row subsets, then CTAs, are combined in a fixed order -> bit-reproducible.
+//
+// Bound: max(HBM, FP64).  k = 20: 336 B and 21 DMMA (10.8 kflop) per row -> 0.22 ms of HBM and 0.30 ms of FP64 for
+// n = 2^22 on a B200.
+#include "device.cuh"
+#include "vs_internal.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include <vector>
+
+namespace vs {
+
+struct MmaGeom {
+    int m, nb, mpad;       // coordinates, 8-wide blocks, padded coordinates
+    int imax;              // block rows that are needed (nb, or 1 without the second-order block)
+    int nsb, nunits;       // super-blocks per side, super-tiles in use
+    int upc, passes;       // super-tiles per CTA, grid.y
+    int rs, warps;         // row subsets per super-tile, consumer warps per CTA
+    int rc, pitch, nstage; // rows per chunk, doubles per staged column, ring depth
+    int second;
+    int sumu;              // position of super-tile (0,0) in the list: its warps also accumulate the shifted sums
+    unsigned char witem[16];   // consumer warp -> work item (super-tile of this pass * rs + row subset), 255 = idle
+    unsigned char ui[128], uj[128];   // super-tile list, heaviest first
+    int hint;              // try_wait suspend-time hint, ns
+    int debug;             // elimination experiments (VS_GRAM_DEBUG): 1 = no Gram update, 2 = no copies
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity, uint32_t hint) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity), "r"(hint)
+        : "memory");
+}
+// global -> shared bulk copy (16-byte aligned on both sides, size a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+
+// The 4-row steps `rsub, rsub + rs, ...` of one staged chunk for the super-tile whose first blocks are (bi0, bj0).
+//   DIAG : row and column operands are the same blocks (only x <= y is needed, and the fragments are shared when `share`).
+//   GUARD: some of the ST x ST blocks may not exist (edge super-tiles, first-order-only mode) -> uniform predicates.
+//   FULL : every row of the chunk is valid (all chunks but the last one) -> no per-lane row predicate.
+// Keep this loop lean: it issues next to the DMMAs (a first version that re-derived `valid` from the kernel arguments for
+// every predicated load ran 376 instructions per step and was issue-bound at 0.89 ms; see profiles/r01_gram_mma_ncu.txt).
+template <int ST, bool DIAG, bool GUARD, bool FULL>
+__device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double &sS, double &sQ, const double *__restrict__ Ya,
+                                          const double *__restrict__ Yb, int colstride, int valid, int rsub, int rs, int lane,
+                                          int xmax, int ymax, int share, bool do_sums, double shiftv) {
+    const int ksteps = (valid + 3) >> 2;
+    const int lrow = lane & 3;
+#pragma unroll 1
+    for (int ks = rsub; ks < ksteps; ks += rs) {
+        const int r0 = ks << 2;
+        const bool rv = FULL || (r0 + lrow < valid);
+        double fa[ST], fb[ST];
+#pragma unroll
+        for (int x = 0; x < ST; ++x) {
+            const bool on = (!GUARD || x < xmax) && rv;
+            fa[x] = 0.0;
+            if (on) fa[x] = Ya[x * colstride + r0];
+        }
+        if (DIAG && (!GUARD || share)) {
+#pragma unroll
+            for (int y = 0; y < ST; ++y) fb[y] = fa[y];
+        } else {
+            // (without the second-order block only block row 0 is loaded on the row side; the column side needs them all)
+#pragma unroll
+            for (int y = 0; y < ST; ++y) {
+                const bool on = (!GUARD || y < ymax) && rv;
+                fb[y] = 0.0;
+                if (on) fb[y] = Yb[y * colstride + r0];
+            }
+        }
+        if (DIAG && do_sums) {
+            const double d = rv ? fa[0] - shiftv : 0.0;      // lanes 0-3: f(M_1) rows, lanes 4-7: f(M_2) rows
+            sS += d;
+            sQ = fma(d, d, sQ);
+        }
+#pragma unroll
+        for (int x = 0; x < ST; ++x)
+#pragma unroll
+            for (int y = DIAG ? x : 0; y < ST; ++y)
+                if (!GUARD || (x < xmax && y < ymax)) dmma(acc[x * ST + y][0], acc[x * ST + y][1], fa[x], fb[y]);
+    }
+}
+
+constexpr int MMA_BAR_DOUBLES = 16;     // full[8] + empty[8]
+constexpr int MMA_MAX_STAGES = 8;
+
+template <int ST, bool MULTI, bool GUARD>        // MULTI: several super-tiles (ST = 4); otherwise one diagonal super-tile
+__global__ void __launch_bounds__(MULTI ? 512 : 384)
+gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, const double *__restrict__ shift,
+                double *__restrict__ blockpart) {
+    extern __shared__ __align__(16) double smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + MMA_MAX_STAGES;
+    double *stages = smem + MMA_BAR_DOUBLES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = g.warps;
+    const int stage_elems = g.mpad * g.pitch;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.nstage; ++s) {
+            bar_init(full + s, 1);
+            bar_init(empty + s, (uint32_t)W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the padded coordinates m .. mpad-1 are never copied: zero them once
+    for (int e = threadIdx.x; e < g.nstage * (g.mpad - g.m) * g.pitch; e += blockDim.x) {
+        const int s = e / ((g.mpad - g.m) * g.pitch), rem = e - s * ((g.mpad - g.m) * g.pitch);
+        stages[(size_t)s * stage_elems + (size_t)g.m * g.pitch + rem] = 0.0;
+    }
+    __syncthreads();
+
+    const uint32_t nchunks = (uint32_t)((rows + g.rc - 1) / g.rc);                 // rows < 2^36 (checked on the host)
+    const uint32_t cnt = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int last_valid = (int)(rows - (uint64_t)(nchunks - 1) * g.rc);          // rows of the last chunk
+
+    double acc[ST * ST][2];
+#pragma unroll
+    for (int t = 0; t < ST * ST; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    double sS = 0.0, sQ = 0.0;
+
+    // work item of this warp: the host spreads the super-tiles over the four sub-partitions by DMMA count (the FP64 pipe is
+    // per sub-partition, and a diagonal or edge super-tile has far fewer 8x8 tiles than an interior one)
+    const int item = warp < W ? g.witem[warp] : 255;
+    const int ul = item == 255 ? 0 : item / g.rs, rsub = item == 255 ? 0 : item - ul * g.rs;
+    const int u = blockIdx.y * g.upc + ul;
+    const bool active = item != 255 && u < g.nunits;
+    const int I = active ? g.ui[u] : 0, J = active ? g.uj[u] : 0;
+
+    if (warp == W) {
+        // ------------------------------------ producer ------------------------------------
+        int s = 0;
+        uint32_t par = 0;
+        uint32_t ch = blockIdx.x;
+        for (uint32_t c = 0; c < cnt; ++c, ch += gridDim.x) {
+            bar_wait(empty + s, par ^ 1u, (uint32_t)g.hint);
+            const uint64_t r0 = (uint64_t)ch * g.rc;
+            const uint32_t valid = ch + 1 == nchunks ? (uint32_t)last_valid : (uint32_t)g.rc;
+            // One elected lane issues every copy from a warp-uniform loop: the operands stay in uniform registers.  (A
+            // lane-strided loop compiles to an ELECT + 5x R2UR + UBLKCP round per lane, ~100 cycles per copy, and the
+            // producer became the bottleneck: 0.89 ms instead of the 0.3 ms FP64 bound at k = 20, n = 2^22.)
+            if (g.debug == 2) {
+                if (lane == 0) bar_arrive(full + s);
+            } else if (elect_one()) {
+                bar_arrive_expect(full + s, (uint32_t)g.m * valid * 8u);
+                double *dst = stages + (size_t)s * stage_elems;
+                const double *src = fvals + r0;
+#pragma unroll 4
+                for (int t = 0; t < g.m; ++t) bulk_g2s(dst + (size_t)t * g.pitch, src + (uint64_t)t * rows, valid * 8u, full + s);
+            }
+            __syncwarp();
+            if (++s == g.nstage) { s = 0; par ^= 1u; }
+        }
+    } else if (warp < W) {
+        // ------------------------------------ consumers -----------------------------------
+        const int foff = (lane >> 2) * g.pitch + (lane & 3);
+        const bool do_sums = active && u == g.sumu;
+        const double shiftv = shift ? *shift : 0.0;
+        const int colstride = 8 * g.pitch;
+        const int xmax = g.imax - ST * I, ymax = g.nb - ST * J;   // blocks of this super-tile that exist (row / column side)
+        const double *Ya0 = stages + foff + (ST * I) * colstride, *Yb0 = stages + foff + (ST * J) * colstride;
+        int s = 0;
+        uint32_t par = 0;
+        uint32_t ch = blockIdx.x;
+        for (uint32_t c = 0; c < cnt; ++c, ch += gridDim.x) {
+            bar_wait(full + s, par, (uint32_t)g.hint);
+            if (active && g.debug != 1) {
+                const double *Ya = Ya0 + (size_t)s * stage_elems, *Yb = Yb0 + (size_t)s * stage_elems;
+                const bool fullc = ch + 1 != nchunks || last_valid == g.rc;
+                auto run = [&](auto diag, auto guard) {
+                    constexpr bool D = decltype(diag)::value, G = decltype(guard)::value;
+                    if (fullc) mma_steps<ST, D, G, true>(acc, sS, sQ, Ya, Yb, colstride, g.rc, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv);
+                    else mma_steps<ST, D, G, false>(acc, sS, sQ, Ya, Yb, colstride, last_valid, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv);
+                };
+                using T_ = std::true_type;
+                using F_ = std::false_type;
+                if constexpr (!MULTI) {
+                    run(T_{}, std::integral_constant<bool, GUARD>{});
+                } else {
+                    const bool interior = g.second && xmax >= ST && ymax >= ST;      // every block of the super-tile exists
+                    if (I == J) { if (interior) run(T_{}, F_{}); else run(T_{}, T_{}); }
+                    else { if (interior) run(F_{}, F_{}); else run(F_{}, T_{}); }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) bar_arrive(empty + s);
+            if (++s == g.nstage) { s = 0; par ^= 1u; }
+        }
+    }
+
+    // ---- combine the row subsets of every super-tile in subset order (every copy has landed: all full barriers were waited on) ----
+    __syncthreads();
+    constexpr int SD = 8 * ST;                                  // super-tile side in coordinates
+    double *img = stages;                                       // [upc][SD][SD]
+    double *sums = img + (size_t)g.upc * SD * SD;               // [rs][8][2]
+    for (int round = 0; round < g.rs; ++round) {
+        if (active && rsub == round) {
+            double *mine = img + (size_t)ul * SD * SD;
+#pragma unroll
+            for (int x = 0; x < ST; ++x)
+#pragma unroll
+                for (int y = 0; y < ST; ++y) {
+                    const int row = 8 * x + (lane >> 2), col = 8 * y + 2 * (lane & 3);   // C fragment: (lane/4, 2*(lane%4)+{0,1})
+                    double *dst = mine + row * SD + col;
+                    if (round == 0) { dst[0] = acc[x * ST + y][0]; dst[1] = acc[x * ST + y][1]; }
+                    else { dst[0] += acc[x * ST + y][0]; dst[1] += acc[x * ST + y][1]; }
+                }
+            if (u == g.sumu && lane < 8) {
+                sums[(round * 8 + lane) * 2 + 0] = sS;
+                sums[(round * 8 + lane) * 2 + 1] = sQ;
+            }
+        }
+        __syncthreads();
+    }
+    const size_t per_block = (size_t)g.mpad * g.mpad + 4;
+    double *bp = blockpart + (size_t)blockIdx.x * per_block;
+    for (int q = 0; q < g.upc; ++q) {
+        const int uq = blockIdx.y * g.upc + q;
+        if (uq >= g.nunits) break;
+        const int Iq = g.ui[uq], Jq = g.uj[uq];
+        for (int e = threadIdx.x; e < SD * SD; e += blockDim.x) {
+            const int row = e / SD, col = e - row * SD;
+            const int gp = SD * Iq + row, gq = SD * Jq + col;
+            if (gp < g.mpad && gq < g.mpad) bp[(size_t)gp * g.mpad + gq] = img[(size_t)q * SD * SD + e];
+        }
+    }
+    if ((int)blockIdx.y == g.sumu / g.upc && threadIdx.x < 4) {
+        // S_A, S_B, Q_A, Q_B: subsets in order, lanes in order
+        const int col = threadIdx.x & 1, which = threadIdx.x >> 1;
+        double s = 0.0;
+        for (int round = 0; round < g.rs; ++round)
+            for (int ln = 0; ln < 4; ++ln) s += sums[(round * 8 + col * 4 + ln) * 2 + which];
+        bp[(size_t)g.mpad * g.mpad + threadIdx.x] = s;
+    }
+}
+
+static __device__ __forceinline__ double sum_blocks(const double *__restrict__ p, size_t stride, int nblocks) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 8 <= nblocks; b += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(b + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < nblocks; ++b) s += p[(size_t)b * stride];
+    return s;
+}
+
+// per-CTA dense images (mpad x mpad + 4 sums) -> packed partial-sum vector, CTA order; entries that were not computed are 0
+__global__ void __launch_bounds__(256) gram_mma_scatter_kernel(int m, int mpad, int pmax, int nblocks, const double *__restrict__ blockpart,
+                                                               double *__restrict__ partials) {
+    const size_t per_block = (size_t)mpad * mpad + 4;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < 4) partials[e] = sum_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
+    if (e >= mpad * mpad) return;
+    const int p = e / mpad, q = e - p * mpad;
+    if (p >= m || q >= m || p > q) return;
+    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = p < pmax ? sum_blocks(blockpart + e, per_block, nblocks) : 0.0;
+}
+
+template <int ST, bool MULTI, bool GUARD>
+static int launch_mma_t(vs_ctx *c, const MmaGeom &g, size_t smem, uint64_t rows, const double *fvals, const double *shift_dev,
+                        double *partials) {
+    auto kern = gram_mma_kernel<ST, MULTI, GUARD>;
+    VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = (g.warps + 1) * 32;
+    int occ = 1;
+    VS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    if (occ > 2) occ = 2;
+    const uint64_t nchunks = (rows + g.rc - 1) / g.rc;
+    int gx = (int)(nchunks < (uint64_t)occ * c->sm_count ? nchunks : (uint64_t)occ * c->sm_count);
+    if (gx < 1) gx = 1;
+    const size_t per_block = (size_t)g.mpad * g.mpad + 4;
+    VS_TRY(ensure(c, c->block_buf, (size_t)gx * per_block * sizeof(double)));
+    time_begin(c);
+    kern<<<dim3(gx, g.passes), threads, smem, c->stream>>>(g, rows, fvals, shift_dev, (double *)c->block_buf.p);
+    time_end(c);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    gram_mma_scatter_kernel<<<(g.mpad * g.mpad + 255) / 256, 256, 0, c->stream>>>(g.m, g.mpad, g.second ? g.m : 8, gx,
+                                                                                 (const double *)c->block_buf.p, partials);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// Returns VS_OK with *handled = true when the tensor path ran; *handled = false means "use gram_kernel".
+int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev, int flags,
+                    double *partials, bool *handled) {
+    *handled = false;
+    if (l != 1 || (rows & 1) || (reinterpret_cast<uintptr_t>(fvals) & 15) || rows == 0) return VS_OK;
+    if (const char *ev = getenv("VS_GRAM_MMA"))
+        if (atoi(ev) == 0) return VS_OK;
+    MmaGeom g{};
+    g.m = 2 + 2 * k;
+    g.nb = (g.m + 7) / 8;
+    g.mpad = 8 * g.nb;
+    g.second = (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0;
+    g.imax = g.second ? g.nb : 1;
+    if (rows >= (1ull << 36)) return VS_OK;
+    // One diagonal super-tile of side ST >= nb when the whole matrix fits one warp's accumulators (k <= 23); otherwise
+    // ST x ST super-tiles, ST in {4, 2} picked by a cost model fitted to B200 measurements (profiles/r01_gram_mma.txt):
+    // a warp retires one DMMA per 60-80 cycles whatever else runs, so a pass costs (8x8 tiles of the heaviest super-tile /
+    // warps sharing it) * that, or the bulk copies of the pass (~2 cycles per coordinate and 4-row step), whichever is larger.
+    const bool multi = g.nb > 6;
+    int ST = g.nb <= 2 ? 2 : g.nb == 3 ? 3 : g.nb == 4 ? 4 : 6;
+    const int maxw = multi ? 15 : 11;        // + 1 producer warp: 16 warps -> 128 registers per thread, 12 warps -> 168
+    if (multi) {
+        double best = 0.0;
+        for (int st : {4, 2}) {
+            const int nsb = (g.nb + st - 1) / st;
+            const int nunits = g.second ? nsb * (nsb + 1) / 2 : nsb;
+            const int upc = nunits < maxw ? nunits : maxw, passes = (nunits + upc - 1) / upc, rs = maxw / upc;
+            const int heavy = (g.second && nsb > 1) ? st * st : st * (st + 1) / 2;
+            const double mma = (double)heavy / rs * (st == 4 ? 60.0 : 80.0), copy = 2.0 * g.m;
+            const double cost = passes * (mma > copy ? mma : copy);
+            if (nunits <= 128 && (best == 0.0 || cost < best)) { best = cost; ST = st; }
+        }
+    }
+    if (const char *ev = getenv("VS_GRAM_ST")) { int v = atoi(ev); if (multi && (v == 2 || v == 4)) ST = v; }      // tuning switch
+    const bool guard = multi || !g.second || g.nb != ST;
+    g.nsb = (g.nb + ST - 1) / ST;
+    g.nunits = g.second ? g.nsb * (g.nsb + 1) / 2 : g.nsb;
+    g.upc = g.nunits < maxw ? g.nunits : maxw;
+    g.passes = (g.nunits + g.upc - 1) / g.upc;
+    g.rs = maxw / g.upc;
+    g.warps = g.upc * g.rs;
+    if (g.nunits > 128) return VS_OK;
+    {
+        // super-tiles, heaviest (most 8x8 tiles) first; then the items of a pass onto the sub-partitions, longest first
+        struct Unit { int I, J, w; };
+        std::vector<Unit> units;
+        for (int I = 0; I < (g.second ? g.nsb : 1); ++I)
+            for (int J = I; J < g.nsb; ++J) {
+                int w = 0;
+                for (int x = 0; x < ST; ++x)
+                    for (int y = 0; y < ST; ++y) {
+                        const int bi = ST * I + x, bj = ST * J + y;
+                        if (bi < g.imax && bj < g.nb && bi <= bj) ++w;
+                    }
+                units.push_back({I, J, w});
+            }
+        std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.w > b.w; });
+        for (int q = 0; q < g.nunits; ++q) {
+            g.ui[q] = (unsigned char)units[q].I;
+            g.uj[q] = (unsigned char)units[q].J;
+            if (units[q].I == 0 && units[q].J == 0) g.sumu = q;
+        }
+        int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+        if (g.warps % 4 == 3) load[3] = 1;                           // the producer warp shares sub-partition (warps % 4)
+        for (int w = 0; w < 16; ++w) g.witem[w] = 255;
+        for (int item = 0; item < g.upc * g.rs; ++item) {
+            const int wt = units[item / g.rs].w;                     // pass 0 decides; later passes have the same shape or lighter
+            int best = -1;
+            for (int sp = 0; sp < 4; ++sp) {
+                const int slot = sp + 4 * used[sp];
+                if (slot >= g.warps) continue;
+                if (best < 0 || load[sp] < load[best]) best = sp;
+            }
+            g.witem[best + 4 * used[best]] = (unsigned char)item;
+            used[best]++;
+            load[best] += wt;
+        }
+    }
+    const size_t avail = c->smem_optin;                       // 227 KB on sm_100a
+    const size_t tail = ((size_t)g.upc * (8 * ST) * (8 * ST) + (size_t)g.rs * 16) * sizeof(double);
+    // rows per chunk: as large as a ~60 KB stage allows (fewer, larger bulk copies and barrier round trips), ring of 3-6 stages
+    int rc_cap = 256;
+    if (const char *ev = getenv("VS_GRAM_RC")) rc_cap = atoi(ev);                            // tuning switch
+    size_t smem = 0;
+    g.nstage = 0;
+    for (int rc : {256, 128, 64, 32}) {
+        if (rc > rc_cap && rc > 32) continue;
+        const size_t stage = (size_t)g.mpad * (rc + 4) * sizeof(double);
+        int ns = (int)((avail - 2048) / stage);                 // one CTA per SM: the ring is what keeps HBM busy
+        if (ns > 6) ns = 6;
+        if ((stage > 60 * 1024 || ns < 3) && rc > 32) continue;
+        if (ns < 2) break;
+        g.rc = rc;
+        g.pitch = rc + 4;
+        g.nstage = ns;
+        smem = MMA_BAR_DOUBLES * sizeof(double) + (size_t)ns * stage;
+        break;
+    }
+    if (g.nstage < 2) return VS_OK;
+    if (const char *ev = getenv("VS_GRAM_STAGES")) { int v = atoi(ev); if (v >= 1 && v < g.nstage) g.nstage = v; }
+    g.hint = getenv("VS_GRAM_HINT") ? atoi(getenv("VS_GRAM_HINT")) : 0x989680;
+    g.debug = getenv("VS_GRAM_DEBUG") ? atoi(getenv("VS_GRAM_DEBUG")) : 0;
+    if (smem < MMA_BAR_DOUBLES * sizeof(double) + tail) smem = MMA_BAR_DOUBLES * sizeof(double) + tail;
+    if (smem > avail) return VS_OK;
+    int rc = VS_OK;
+#define VS_MMA_CASE(S, M, G) rc = launch_mma_t<S, M, G>(c, g, smem, rows, fvals, shift_dev, partials)
+    if (multi) { if (ST == 4) VS_MMA_CASE(4, true, true); else VS_MMA_CASE(2, true, true); }
+    else if (ST == 2) { if (guard) VS_MMA_CASE(2, false, true); else VS_MMA_CASE(2, false, false); }
+    else if (ST == 3) { if (guard) VS_MMA_CASE(3, false, true); else VS_MMA_CASE(3, false, false); }
+    else if (ST == 4) { if (guard) VS_MMA_CASE(4, false, true); else VS_MMA_CASE(4, false, false); }
+    else { if (guard) VS_MMA_CASE(6, false, true); else VS_MMA_CASE(6, false, false); }
+#undef VS_MMA_CASE
+    if (rc == VS_OK) *handled = true;
+    return rc;
+}
+
+}  // namespace vs

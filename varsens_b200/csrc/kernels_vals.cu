@@ -322,6 +322,9 @@ int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double 
 int launch_partials_from_values(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev,
                                 int flags, double *partials) {
     int plen = (int)vs_partials_len(k, l);
+    bool handled = false;
+    VS_TRY(launch_gram_mma(c, k, l, rows, fvals, shift_dev, flags, partials, &handled));
+    if (handled) return VS_OK;
     GramGeom best = make_geom(k, l, flags, 4);
     for (int T : {6, 8}) {
         GramGeom g = make_geom(k, l, flags, T);

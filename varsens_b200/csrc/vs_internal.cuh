@@ -152,6 +152,9 @@ size_t result_len(int k, int l);
 int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world, int rank, const uint64_t *peer_bufs_dev,
                                const uint64_t *peer_flags_dev, uint32_t epoch, const double *partials, int flags, double *res_dev);
 int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
+// kernels_gram_mma.cu: tensor-path Gram for l == 1 (*handled = false -> caller falls back to gram_kernel)
+int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev, int flags,
+                    double *partials, bool *handled);
 // kernels_fused.cu
 bool fused_supported(int k, int objective, int flags);
 int launch_fused(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
