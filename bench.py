@@ -291,6 +291,25 @@ def run_gpu(args, rank, world):
     ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if sampler else None          # sampled over both timed regions
 
+    # index time: from "partial sums of every rank ready" to the indices on the host = all-reduce + finalize +
+    # D2H; and, single GPU, from "all 2n(1+k) values resident" to the indices on the host (vs_indices_from_values path).
+    def step_index():
+        if world > 1:
+            vdist.allreduce_partials(part)
+        ctx.finalize_device(k, 1, n, part, res_dev, flags)
+        return _cabi.Result.from_flat(k, 1, res_dev.cpu().numpy())
+    part_keep = part.clone()
+    index_ms, _ = timed(step_index, args.steps, 3)
+    part.copy_(part_keep)
+    index_values_ms = None
+    if world == 1:
+        try:
+            vals = torch.rand((2 + 2 * k) * n, dtype=torch.float64, device=dev)          # 5.6 GB of stand-in values, flat() order
+            index_values_ms, _ = timed(lambda: ctx.indices_from_values(k, 1, n, n, vals, flags=flags), max(3, args.steps // 2), 3)
+            del vals
+        except Exception as exc:                                                         # extra figure only; never fail the bench on it
+            index_values_ms = "failed: %s" % (str(exc).splitlines()[0][:80],)
+
     # fused kernel alone (this rank's shard), separable shortcut for context
     sep_ms = None
     if world == 1:
@@ -320,10 +339,13 @@ def run_gpu(args, rank, world):
         "config": {"workload": "C3 Sobol g-function k=20 n=2^24 identity scaling, fused generic functor, second order on",
                    "k": k, "n": n, "evals_per_step": evals(n), "parallelism": "rows sharded over %d rank(s), 1 all-reduce of %d doubles (%s)" % (world, plen, "fused peer-memory kernel over NVLink" if (world > 1 and os.environ.get("VS_P2P", "0") == "1" and vdist.peer_exchange(plen, dev) is not None) else "NCCL" if world > 1 else "none"),
                    "l2": "192 MiB buffer written between timed iterations (L2 flush)", "index_time_ms": "included (finalize kernel + D2H of %d doubles)" % (6 * k + 2 + 2 * k * k), "resident_step": mode},
+        "index_time": {"partials_to_host_indices_ms": index_ms, "what": "%sfinalize kernel + D2H of the indices, timed alone" % ("NCCL all-reduce of the partial sums + " if world > 1 else ""),
+                       "values_to_host_indices_ms": index_values_ms, "values_what": "vs_indices_from_values on 2n(1+k) = %d resident values (bulk-copy + DMMA Gram kernel)" % evals(n)},
         "e2e": {"value": evals(n) / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k))},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+        # "tensor" = compute bound; the pipe is FP64: evaluation on DFMA, Gram on DMMA (mma.sync m8n8k4.f64), which share one datapath
+        "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA + DMMA share one 36-37 TFLOP/s datapath on B200)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel (ncu --set full at n=2^22: 16.94 MB read, 0 written
                      # = the uint32 permutation; profiles/r01_fused_v3_wsd_ncu_summary.txt), scaled to this rank's rows
                      "traffic": 16.942592e6 * rows_rank0 / float(1 << 22), "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, 3, 1> (12 E-warps + 4 S-warps per SM, DMMA Gram)", "kernel_ms": kms,
@@ -355,6 +377,7 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION prints there otherwise)
     if args.impl == "reference":
         return run_reference(args, rank)
     if args.warmup < 3:
