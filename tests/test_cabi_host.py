@@ -165,3 +165,25 @@ def test_sobol_direction_numbers_match_oracle():
     from varsens_b200 import sobol as vsobol
     from oracle import sobol as osobol
     assert (vsobol.joe_kuo_direction_numbers(40) == osobol.joe_kuo_direction_numbers(40)).all()
+
+
+def test_objective_binary_batches_round_trip(tmp_path):
+    """Objective.export/load with postfix='.npy' (SURVEY.md §8f.2): host-only path, exact round trip, and the
+    reference's text format still reads back to 17 significant digits."""
+    import math
+    import varsens_b200 as vb
+    k, n = 3, 40
+    rng = numpy.random.RandomState(5)
+    vals = rng.rand(2 * n * (1 + k), 2)
+    o = vb.Objective(k, n, objective_vals=vals, verbose=False)
+    o.export(str(tmp_path), "obj", ".npy", 100)
+    nfiles = int(math.ceil(len(vals) / 100.0))
+    assert sorted(p.name for p in tmp_path.iterdir()) == sorted("obj_%d.npy" % (i + 1) for i in range(nfiles))
+    o2 = vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="obj", postfix=".npy", nFiles=nfiles)
+    assert (o2.flat() == vals).all()
+    assert (o2.fN_nj == o.fN_nj).all() and o2.fN_j.shape == (k, n, 2)
+    o.export(str(tmp_path), "objt", ".txt", 100)
+    o3 = vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="objt", postfix=".txt", nFiles=nfiles)
+    assert (o3.flat() == vals).all()           # %.18e round-trips a double exactly
+    with pytest.raises(Exception, match="Cannot find input file"):
+        vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="nope", postfix=".npy", nFiles=1)

@@ -456,6 +456,17 @@ def test_api_export_load_round_trip(vb, tmp_path, refgold, capsys):
         numpy.testing.assert_allclose(getattr(v2, name), getattr(v, name), rtol=0, atol=5e-8)    # 7 places, as the reference test
     s2 = vb.Sample(k, n, verbose=False, indir=str(tmp_path), prefix="batch", postfix=".csv", nFiles=nfiles)
     assert (s2.M_2 == s.M_2).all() and (s2.N_nj == s.N_nj).all()
+    # binary batches (.npy): same file naming and row windows, bit-exact both ways
+    s.export(str(tmp_path), "bin", ".npy", 3000)
+    nbin = int(math.ceil(2 * n * (1 + k) / 3000.0))
+    first = numpy.load(str(tmp_path / "bin_1.npy"))
+    assert first.shape == (3000, k) and (first == s.flat()[:3000]).all()
+    s3 = vb.Sample(k, n, verbose=False, indir=str(tmp_path), prefix="bin", postfix=".npy", nFiles=nbin)
+    assert (s3.M_1 == s.M_1).all() and (s3.N_j == s.N_j).all()
+    v.objective.export(str(tmp_path), "objbin", ".npy", 5000)
+    o4 = vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="objbin", postfix=".npy",
+                      nFiles=int(math.ceil(2 * n * (1 + k) / 5000.0)))
+    assert (o4.flat() == v.objective.flat()).all()
     o3 = vb.Objective(6, 256, objective_vals=refgold["nan_obj_in"], verbose=False)
     assert tuple(o3.fM_1.shape) == tuple(refgold["nan_fM_1_shape"])
     v3 = vb.Varsens(o3, verbose=False)
