@@ -353,7 +353,9 @@ def run_gpu(args, rank, world):
                      "peak_source": "DFMA-chain microbenchmark run in this process (vs_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"},
         "clocks": clocks,
         "check": {"var_y": float(res.var_y[0]), "E_2": float(res.E_2[0]), "sens0": float(res.sens[0, 0]),
-                  "e2e_equals_resident": bool(numpy.array_equal(res.sens, res2.sens))},
+                  # e2e adds the chunk partial sums of the pipelined H2D path in chunk order: same indices up to summation order
+                  "e2e_matches_resident": bool(numpy.allclose(res.sens, res2.sens, rtol=1e-11, atol=1e-13)),
+                  "e2e_max_abs_diff_sens": float(numpy.max(numpy.abs(res.sens - res2.sens)))},
     }
     if sep_ms is not None:
         line["separable_shortcut"] = {"value": evals(n) / (sep_ms * 1e-3), "unit": UNIT, "ms_per_step": sep_ms,

@@ -316,6 +316,27 @@ def test_fused_shards_equal_whole(ctx):
     assert_indices(ctx.finalize(k, 1, n, acc), cport.run(k, n, cport.OBJ_GFUNCTION, A20))
 
 
+def test_fused_host_permutation_is_pipelined_and_agrees(ctx, monkeypatch):
+    """vs_run_fused / vs_fused_partials with a HOST permutation of >= 2^21 rows cut the H2D copy into chunks and launch the
+    fused kernel per chunk (abi.cu: fused_partials_pipelined).  Same indices as the all-device call (chunk sums are added
+    in chunk order, so the last bits may differ), reproducible, and identical to the unpipelined host path per chunk."""
+    import torch
+    k, n = 6, 1 << 22
+    perm = perm_of(n)
+    dev = ctx.run_fused(k, n, torch.from_numpy(perm.astype(numpy.int32)).cuda(), cport.OBJ_GFUNCTION, A6)
+    host = ctx.run_fused(k, n, perm, cport.OBJ_GFUNCTION, A6)
+    host2 = ctx.run_fused(k, n, perm, cport.OBJ_GFUNCTION, A6)
+    for name in NAMES:
+        close(getattr(host, name), getattr(dev, name), rel=1e-11, abs_=1e-12)
+        assert (getattr(host, name) == getattr(host2, name)).all()
+    # a shard with a host permutation: [n/4, n) = 3 * 2^20 rows -> 3 chunks
+    lo = n // 4
+    a = ctx.fused_partials(k, n, perm, cport.OBJ_GFUNCTION, A6, i_begin=lo, i_end=n)
+    monkeypatch.setenv("VS_NO_PIPELINE", "1")
+    b = ctx.fused_partials(k, n, perm, cport.OBJ_GFUNCTION, A6, i_begin=lo, i_end=n)
+    numpy.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)
+
+
 def test_fused_ishigami(ctx):
     from varsens_b200 import _cabi
     pi = math.pi

@@ -4,6 +4,8 @@
 
 #include "vs_internal.cuh"
 
+#include <cstdlib>
+
 using namespace vs;
 
 namespace {
@@ -229,9 +231,67 @@ extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint6
     return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
 }
 
+// Sum of `nchunk` partial-sum vectors in chunk order (fixed order -> reproducible).
+__global__ void __launch_bounds__(256) sum_chunks_kernel(int plen, int nchunk, const double *__restrict__ in, double *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= plen) return;
+    double s = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) s += in[(size_t)ch * plen + e];
+    out[e] = s;
+}
+
+// Host permutation + fused kernel: the H2D copy of the permutation (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over
+// PCIe) is cut into chunks on the copy stream and the fused kernel is launched per chunk as its slice arrives, so only the
+// first slice is exposed.  Chunk partial sums are added in chunk order.  (vs_run_fused / vs_fused_partials with VS_MEM_HOST.)
+static const uint64_t PIPE_MIN_ROWS = 1ull << 21;
+
+static int fused_partials_pipelined(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm_host, const vs_scale *scale,
+                                    int objective, const double *params, int n_params, uint64_t i_begin, uint64_t i_end, int flags,
+                                    double *partials_dev) {
+    const uint64_t rows = i_end - i_begin;
+    int nchunk = (int)(rows >> 20);
+    if (nchunk > 8) nchunk = 8;
+    const size_t plen = vs_partials_len(k, 1);
+    VS_TRY(ensure(c, c->perm_buf, rows * sizeof(uint32_t)));
+    VS_TRY(ensure(c, c->pipe_buf, (size_t)nchunk * plen * sizeof(double)));
+    while ((int)c->pipe_ev.size() < nchunk + 1) {
+        cudaEvent_t e;
+        VS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_ev.push_back(e);
+    }
+    SourceDev src;
+    const uint32_t *perm_dev = (const uint32_t *)c->perm_buf.p - i_begin;          // indexed by the absolute base row
+    VS_TRY(make_source(c, k, n, discard, perm_dev, VS_MEM_DEVICE, i_begin, rows, nullptr, VS_MEM_HOST, &src));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    ObjectiveDev od;
+    VS_TRY(get_objective(c, k, objective, params, n_params, &od));
+    // the copies may not overwrite the staging buffer before earlier work on the compute stream has finished reading it
+    VS_CUDA(cudaEventRecord(c->pipe_ev[nchunk], c->stream));
+    VS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[nchunk], 0));
+    auto bound = [&](int ch) { return i_begin + rows * (uint64_t)ch / (uint64_t)nchunk; };
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const uint64_t b = bound(ch), e = bound(ch + 1);
+        VS_CUDA(cudaMemcpyAsync((uint32_t *)c->perm_buf.p + (b - i_begin), perm_host + b, (e - b) * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, c->copy_stream));
+        VS_CUDA(cudaEventRecord(c->pipe_ev[ch], c->copy_stream));
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        VS_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_ev[ch], 0));
+        VS_TRY(launch_fused(c, k, src, s, od, bound(ch), bound(ch + 1), flags, (double *)c->pipe_buf.p + (size_t)ch * plen));
+    }
+    sum_chunks_kernel<<<(unsigned)((plen + 255) / 256), 256, 0, c->stream>>>((int)plen, nchunk, (const double *)c->pipe_buf.p, partials_dev);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
 static int fused_partials_dev(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
                               const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
                               int n_params, uint64_t i_begin, uint64_t i_end, int flags, double *partials_dev) {
+    if (perm_mem == VS_MEM_HOST && !raw && i_end - i_begin >= PIPE_MIN_ROWS && fused_supported(k, objective, flags) && !capturing(c) &&
+        !getenv("VS_NO_PIPELINE"))
+        return fused_partials_pipelined(c, k, n, discard, perm, scale, objective, params, n_params, i_begin, i_end, flags, partials_dev);
     SourceDev src;
     VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, i_end - i_begin, raw, raw_mem, &src));
     ScaleDev s;

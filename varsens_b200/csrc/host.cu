@@ -53,7 +53,7 @@ int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, c
     return VS_OK;
 }
 
-static bool capturing(vs_ctx *c) {
+bool capturing(vs_ctx *c) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(c->stream, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
     return st != cudaStreamCaptureStatusNone;
@@ -298,6 +298,7 @@ extern "C" int vs_ctx_destroy(vs_ctx *c) {
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->halton.blob) cudaFree(c->halton.blob);
+    for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);

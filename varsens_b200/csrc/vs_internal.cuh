@@ -120,6 +120,8 @@ struct vs_ctx {
     vs::DevBuf peer_buf;
     int scale_kind_cached = -1, scale_k_cached = -1, obj_id_cached = -1;
     // scratch
+    std::vector<cudaEvent_t> pipe_ev;    // chunk-arrival events of the pipelined host-permutation path
+    vs::DevBuf pipe_buf;
     vs::DevBuf scale_buf, obj_buf, perm_buf, raw_buf, io_buf, part_buf, block_buf, res_buf, dir_buf, misc_buf;
 };
 
@@ -133,6 +135,7 @@ int get_objective(vs_ctx *c, int k, int objective, const double *params, int n_p
 int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, const void **dev);
 int make_source(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
                 uint64_t perm_begin, uint64_t perm_count, const double *raw, int raw_mem, SourceDev *out);
+bool capturing(vs_ctx *c);
 void time_begin(vs_ctx *c);
 void time_end(vs_ctx *c);
 
