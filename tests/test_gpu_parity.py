@@ -261,10 +261,11 @@ def test_partials_shards_sum_to_whole(ctx):
 # fused pipeline
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,n", [(2, 2), (2, 33), (3, 1000), (4, 64), (5, 31), (6, 1024), (8, 500), (10, 999), (12, 256),
-                                 (16, 77), (20, 4096), (7, 300), (24, 200)])
+                                 (16, 77), (20, 4096), (7, 300), (9, 130), (11, 257), (13, 64), (14, 100), (15, 333),
+                                 (17, 96), (18, 40), (19, 1000), (24, 200), (1, 50)])
 def test_fused_gfunction_matches_oracle(ctx, k, n):
     a = (A20 + [1.0, 2.0, 5.0, 99.0])[:k]
-    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, a)          # k=7, 24: two-phase path inside the library
+    res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_GFUNCTION, a)          # k=1, 24: two-phase path inside the library
     assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, a))
 
 
