@@ -187,3 +187,27 @@ def test_objective_binary_batches_round_trip(tmp_path):
     assert (o3.flat() == vals).all()           # %.18e round-trips a double exactly
     with pytest.raises(Exception, match="Cannot find input file"):
         vb.Objective(k, n, verbose=False, indir=str(tmp_path), prefix="nope", postfix=".npy", nFiles=1)
+
+
+def test_reference_permutation_cache_keeps_rng_side_effect():
+    """saltelli.py:100-101 reseeds and advances numpy's GLOBAL legacy RNG; the cached permutation must leave it in the
+    same state as a fresh draw, and equal the oracle's permutation."""
+    from varsens_b200 import saltelli as vsalt
+    vsalt._perm_cache.clear()
+    for n in (1000, 1, 2, 4097):
+        numpy.random.seed(12345)
+        first = vsalt._reference_permutation(n)
+        after_first = numpy.random.random_sample(3)
+        numpy.random.seed(999)
+        again = vsalt._reference_permutation(n)                 # cache hit
+        after_again = numpy.random.random_sample(3)
+        idx = numpy.arange(n)
+        numpy.random.seed(1)
+        numpy.random.shuffle(idx)
+        want_after = numpy.random.random_sample(3)
+        assert (first == idx).all() and again is first and first.dtype == numpy.uint32
+        assert (first == pipeline.permutation(n)).all()
+        assert (after_first == want_after).all() and (after_again == want_after).all()
+    for n in range(10, 20):                                      # bounded: only the newest few are kept
+        vsalt._reference_permutation(n)
+    assert len(vsalt._perm_cache) <= 4

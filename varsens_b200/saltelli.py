@@ -22,13 +22,28 @@ def _say(verbose, *a, **kw):
         print(*a, **kw)
 
 
+_perm_cache = {}          # n -> (uint32 permutation, global numpy RNG state after drawing it); a few entries, newest last
+
+
 def _reference_permutation(n):
     """The row order ``numpy.random.seed(1); numpy.random.shuffle(M_2)`` produces (saltelli.py:100-101),
-    drawn from the same global legacy RNG with the same side effect on its state."""
-    idx = numpy.arange(int(n))
+    drawn from the same global legacy RNG with the same side effect on its state.  The order depends on n only
+    (the seed is fixed), and the Fisher-Yates walk is serial (~1 s at n = 2^24, 200x the GPU work that follows), so
+    the last few permutations are kept; a cache hit restores the RNG state the reference call would have left."""
+    n = int(n)
+    hit = _perm_cache.get(n)
+    if hit is not None:
+        numpy.random.set_state(hit[1])
+        return hit[0]
+    idx = numpy.arange(n)
     numpy.random.seed(1)
     numpy.random.shuffle(idx)
-    return idx.astype(numpy.uint32)
+    perm = idx.astype(numpy.uint32)
+    perm.setflags(write=False)
+    while len(_perm_cache) >= 4:
+        _perm_cache.pop(next(iter(_perm_cache)))
+    _perm_cache[n] = (perm, numpy.random.get_state())
+    return perm
 
 
 class Sample(object):
