@@ -93,7 +93,11 @@ int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offs
 /* Length of the partial-sum vector for k factors and l outputs: 4l + m(m+1)/2, m = (2+2k) l.
  * Layout: S_A[l], S_B[l], Q_A[l], Q_B[l] (sums / sums of squares of fM_1 - c, fM_2 - c for a
  * common shift c), then the upper triangle (row-major, t <= u) of G[t][u] = sum_i v_i[t] v_i[u]
- * with v_i = (fM_1[i], fM_2[i], fN_j[0..k)[i], fN_nj[0..k)[i]) x outputs, index t*l + o. */
+ * with v_i = (fM_1[i], fM_2[i], fN_j[0..k)[i], fN_nj[0..k)[i]) x outputs, index t*l + o.
+ * vs_fused_partials may deliver the second-order blocks SYMMETRISED (J_j = fN_j[j], N_j = fN_nj[j]):
+ *   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2  and  G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
+ * i.e. exactly the combinations vs_finalize adds up (saltelli.py:612-613, 618-619); vectors from
+ * vs_partials_from_values hold the plain entries.  Both kinds add up across shards and ranks. */
 size_t vs_partials_len(int k, int l);
 
 /* ---- generators ---------------------------------------------------------------------------- */

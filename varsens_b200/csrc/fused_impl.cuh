@@ -284,18 +284,40 @@ constexpr int EG = VS_EG;
 template <int K>
 __host__ __device__ constexpr int eval_groups() { return (2 + 2 * K + EG - 1) / EG; }
 
-template <int K, class F, int G, class YR>
+// ---- paired tile layout ------------------------------------------------------------------------------------------
+// The second-order estimators read the J/N blocks of the Gram only in the symmetric combinations
+//   N_i.N_j + J_i.J_j  (saltelli.py:618-619)   and   N_i.J_j + J_i.N_j  (:612-613),      J_j = f(N_j[j]), N_j = f(N_nj[j]),
+// and with P = N + J, M = N - J these are (P_i.P_j + M_i.M_j)/2 and (P_i.P_j - M_i.M_j)/2; the first-order sums follow from
+// A.P_j, A.M_j, B.P_j, B.M_j.  So instead of the Gram of the (2+2K)-vector (A, B, J, N) the S-warps accumulate the Grams
+// of the two (K+2)-vectors  w = (P_0..P_{K-1}, A, B)  and  u = (M_0..M_{K-1}, A, B):  2 * HB(HB+1)/2 8x8 tiles with
+// HB = ceil((K+2)/8) instead of NB(NB+1)/2 with NB = ceil((2+2K)/8) -- 12 instead of 21 DMMA per 4 rows at K = 20.
+// The E-warp forms P_j, M_j when both members of a pair are evaluated (2 extra DADD per pair); pm_scatter_kernel maps
+// the CTA sums back to the packed partial-sum vector (second-order blocks symmetrised, see include/varsens_b200.h).
+template <int K> __host__ __device__ constexpr int pm_hb() { return (K + 2 + 7) / 8; }
+template <int K> __host__ __device__ constexpr bool pm_pays() {
+    constexpr int nb = (2 + 2 * K + 7) / 8, hb = (K + 2 + 7) / 8;
+    return hb * (hb + 1) < nb * (nb + 1) / 2;
+}
+
+// Evaluation slot E -> design point.  Plain order: E = p.  Paired order: A, B, then (N_j[j], N_nj[j]) for j = 0, 1, ...
+template <int K, bool PM> __host__ __device__ constexpr int point_of_slot(int E) {
+    return (!PM || E < 2) ? E : (((E - 2) & 1) ? 2 + K + (E - 2) / 2 : 2 + (E - 2) / 2);
+}
+
+template <int K, class F, int G, bool PM, class YR>
 __device__ __forceinline__ void eval_group(const F &f, const double (&tk)[EG], const double (&a)[K], const double (&b)[K], bool valid,
                                            const YR &Yrow, double &fA, double &fB) {
+    static_assert(!PM || EG % 2 == 0, "paired layout needs both members of a pair in one evaluation group");
     constexpr int M = 2 + 2 * K;
     constexpr int P0 = G * EG;
     constexpr int NP = (M - P0) < EG ? (M - P0) : EG;
+    constexpr int HS = 8 * pm_hb<K>();
     double pr[NP] = {};
     static_for<K>([&](auto Cc) {
         constexpr int C = decltype(Cc)::value;
         static_for<NP>([&](auto Uc) {
             constexpr int U = decltype(Uc)::value;
-            constexpr int P = P0 + U;
+            constexpr int P = point_of_slot<K, PM>(P0 + U);
             // point P: 0 = A_i, 1 = B_i, 2+J = B_i with column J from A_i, 2+K+J = A_i with column J from B_i
             constexpr bool fromA = (P == 0) || (P >= 2 && P < 2 + K && C == P - 2) || (P >= 2 + K && C != P - 2 - K);
             const double s_ = f.factor(C, fromA ? a[C] : b[C], tk[U]);
@@ -304,11 +326,16 @@ __device__ __forceinline__ void eval_group(const F &f, const double (&tk)[EG], c
     });
     static_for<NP>([&](auto Uc) {
         constexpr int U = decltype(Uc)::value;
-        constexpr int P = P0 + U;
-        const double v = f.finish(pr[U]);
-        if constexpr (P == 0) fA = v;
-        else if constexpr (P == 1) fB = v;
-        else Yrow[P] = valid ? v : 0.0;
+        constexpr int P = point_of_slot<K, PM>(P0 + U);
+        if constexpr (P == 0) fA = f.finish(pr[U]);
+        else if constexpr (P == 1) fB = f.finish(pr[U]);
+        else if constexpr (!PM) Yrow[P] = valid ? f.finish(pr[U]) : 0.0;
+        else if constexpr (P >= 2 + K) {                           // second member of pair j: slot U-1 holds f(N_j[j])
+            constexpr int J = P - 2 - K;
+            const double vj = f.finish(pr[U - 1]), vn = f.finish(pr[U]);
+            Yrow[J] = valid ? vn + vj : 0.0;
+            Yrow[HS + J] = valid ? vn - vj : 0.0;
+        }
     });
 }
 
@@ -319,7 +346,7 @@ struct YRef {                                  // value p of a lane's row lives 
 };
 
 // ---- phase 1b: evaluate the functor on the 2+2k points of the lane's row; values go to Yrow ----
-template <int K, class F, bool SEPARABLE>
+template <int K, class F, bool SEPARABLE, bool PM = false>
 __device__ __forceinline__ void eval_rows(const F &f, volatile double *tokp, const double (&a)[K], const double (&b)[K],
                                           bool valid, double *__restrict__ Ybase, double shift, double &sA, double &qA,
                                           double &sB, double &qB, const int ystride = 1) {
@@ -363,9 +390,10 @@ __device__ __forceinline__ void eval_rows(const F &f, volatile double *tokp, con
             double tk[EG];
 #pragma unroll
             for (int u = 0; u < EG; ++u) tk[u] = *tokp;
-            eval_group<K, F, decltype(Gc)::value>(f, tk, a, b, valid, Yrow, fA, fB);
+            eval_group<K, F, decltype(Gc)::value, PM>(f, tk, a, b, valid, Yrow, fA, fB);
         });
     } else {
+        static_assert(!PM, "paired layout is implemented for product-form functors");
         fA = f(a, *tokp);
         fB = f(b, *tokp);
         static_for<K>([&](auto Jc) {
@@ -381,8 +409,15 @@ __device__ __forceinline__ void eval_rows(const F &f, volatile double *tokp, con
             Yrow[2 + K + J] = valid ? vn : 0.0;
         });
     }
-    Yrow[0] = valid ? fA : 0.0;
-    Yrow[1] = valid ? fB : 0.0;
+    if constexpr (PM) {
+        static_assert(!(SEPARABLE && F::separable), "the prefix/suffix shortcut keeps the plain layout");
+        constexpr int HS = 8 * pm_hb<K>();
+        Yrow[K] = Yrow[HS + K] = valid ? fA : 0.0;
+        Yrow[K + 1] = Yrow[HS + K + 1] = valid ? fB : 0.0;
+    } else {
+        Yrow[0] = valid ? fA : 0.0;
+        Yrow[1] = valid ? fB : 0.0;
+    }
     if (valid) {
         double dA = fA - shift, dB = fB - shift;
         sA += dA;
@@ -558,15 +593,40 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+template <int K, class F, bool SEPARABLE>
+__host__ __device__ constexpr bool wsd_paired() { return pm_pays<K>() && F::separable && !SEPARABLE; }
+
+// Upper-triangular tile walk shared by the S-warp update, the combine step and nothing else: fn(t, P, Q) with block
+// coordinates inside the padded tile row (paired layout: two independent triangles).
+template <int NB, int HB, bool PM, class Fn>
+__device__ __forceinline__ void for_each_tile(Fn &&fn) {
+    int t = 0;
+    if constexpr (PM) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int P = 0; P < HB; ++P)
+#pragma unroll
+                for (int Q = P; Q < HB; ++Q, ++t) fn(t, h * HB + P, h * HB + Q);
+    } else {
+#pragma unroll
+        for (int P = 0; P < NB; ++P)
+#pragma unroll
+            for (int Q = P; Q < NB; ++Q, ++t) fn(t, P, Q);
+    }
+}
+
 template <int K, class F, bool SEPARABLE, int EPS, int NBUF>
 __global__ void __launch_bounds__((EPS + 1) * WS_S * 32, 1)
 fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, const double *__restrict__ shift_ptr,
                  double *__restrict__ blockpart) {
     constexpr int WS_E = EPS * WS_S;
     constexpr int M = 2 + 2 * K;
-    constexpr int NB = (M + 7) / 8;                     // 8-wide blocks
+    constexpr bool PM = wsd_paired<K, F, SEPARABLE>();  // paired tile layout (see pm_pays)
+    constexpr int HB = pm_hb<K>();
+    constexpr int NB = PM ? 2 * HB : (M + 7) / 8;       // 8-wide blocks of a tile row
     constexpr int MPAD = NB * 8;
-    constexpr int NTL = NB * (NB + 1) / 2;              // upper-triangular 8x8 tiles
+    constexpr int NTL = PM ? HB * (HB + 1) : NB * (NB + 1) / 2;    // 8x8 tiles: two upper triangles / one
     constexpr int TILE = MPAD * YT_PITCH;               // doubles per Y tile
 
     extern __shared__ double smem[];
@@ -613,73 +673,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         // a warp that generates while the others evaluate finds the LSU free, finishes early and catches up -- and
         // then the two phases add up (clock stamps: 12.6k + 10.5k cycles per batch).  A named barrier over the E-warps
         // after every phase pins team 0 to "generate" while team 1 "evaluates" and vice versa.
-        // ---- rotating schedule (EPS == 3, product-form generic path; fc.rotate) --------------------------------------
-        // The three E-warps of a sub-partition are pinned to three different phases by a named barrier after every slot:
-        //   team (s mod 3)   : GENERATE its next batch        (integer + shared-memory pipe, 4 warps per SM at a time)
-        //   the other two    : first / second half of their EVALUATION (two warps share the FP64 pipe and hide its latency)
-        // so one batch per sub-partition completes per slot and generation always runs under evaluation.  Without the
-        // barrier the warps drift into lock-step (all generate, then all evaluate) and the two phases add up.
-        bool rotated = false;
-        if constexpr (EPS == 3 && F::separable && !SEPARABLE) {
-            if (fc.rotate && fc.debug == 0) {
-                rotated = true;
-                auto rbar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
-                const int team = e / WS_S;
-                const uint64_t nslots = 3 * count_of(0) + 2;            // count_of(0) is the largest batch count in the CTA
-                constexpr int NE = eval_groups<K>(), NE1 = (NE + 1) / 2;
-                double a[K], b[K];
-                bool valid = false;
-                double fA = 0.0, fB = 0.0;
-                uint64_t it = 0;
-                for (uint64_t sl = 0; sl < nslots; ++sl) {
-                    const int q = (int)((sl + 3 - team) % 3);
-                    if (sl >= (uint64_t)team && it < cnt) {
-                        const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 64;
-                        long long *trp = fc.trace + ((size_t)warp * 64 + (it < 64 ? it : 0)) * 4;
-                        const YRef Yrow{tiles + (size_t)e * TILE + lane, YT_PITCH};
-                        if (q == 0) {
-                            if (tr_on) trp[0] = clock64();
-                            valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
-                                a[d] = xa;
-                                b[d] = xb;
-                            });
-                            if (tr_on) trp[1] = clock64();
-                        } else if (q == 1) {
-                            mbar_wait(empty_bar(e, 0), (uint32_t)((it & 1) ^ 1));
-                            if (tr_on) trp[2] = clock64();
-                            static_for<NE1>([&](auto Gc) {
-                                double tk[EG];
-#pragma unroll
-                                for (int u = 0; u < EG; ++u) tk[u] = *tokp;
-                                eval_group<K, F, decltype(Gc)::value>(f, tk, a, b, valid, Yrow, fA, fB);
-                            });
-                        } else {
-                            static_for<NE - NE1>([&](auto Gc) {
-                                double tk[EG];
-#pragma unroll
-                                for (int u = 0; u < EG; ++u) tk[u] = *tokp;
-                                eval_group<K, F, NE1 + decltype(Gc)::value>(f, tk, a, b, valid, Yrow, fA, fB);
-                            });
-                            Yrow[0] = valid ? fA : 0.0;
-                            Yrow[1] = valid ? fB : 0.0;
-                            if (valid) {
-                                double dA = fA - shift, dB = fB - shift;
-                                sA += dA;
-                                qA = fma(dA, dA, qA);
-                                sB += dB;
-                                qB = fma(dB, dB, qB);
-                            }
-                            __syncwarp();
-                            if (tr_on) trp[3] = clock64();
-                            if (lane == 0) mbar_arrive(full_bar(e, 0));
-                            ++it;
-                            bt += G;
-                        }
-                    }
-                    rbar();
-                }
-            }
-        }
+        constexpr bool rotated = false;      // (a barrier-pinned generate/evaluate/evaluate rotation was measured at 6.08 ms vs 5.23 and removed)
         const bool alternate = (EPS == 2) && fc.alternate;
         auto ebar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
         const int team = e / WS_S;
@@ -711,7 +705,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 #pragma unroll
                 for (int d = 0; d < K; ++d) { Y[lane + (2 + d) * YT_PITCH] = a[d]; Y[lane + (2 + K + d) * YT_PITCH] = b[d]; }
             } else {
-                eval_rows<K, F, SEPARABLE>(f, tokp, a, b, valid, Y + lane, shift, sA, qA, sB, qB, YT_PITCH);
+                eval_rows<K, F, SEPARABLE, PM>(f, tokp, a, b, valid, Y + lane, shift, sA, qA, sB, qB, YT_PITCH);
             }
             __syncwarp();
             if (tr_on) trp[3] = clock64();
@@ -750,11 +744,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
                     double fr[NB];
 #pragma unroll
                     for (int P = 0; P < NB; ++P) fr[P] = Y[P * 8 * YT_PITCH + r0];
-                    int t = 0;
-#pragma unroll
-                    for (int P = 0; P < NB; ++P)
-#pragma unroll
-                        for (int Q = P; Q < NB; ++Q, ++t) dmma_m8n8k4(acc[t][0], acc[t][1], fr[P], fr[Q]);
+                    for_each_tile<NB, HB, PM>([&](int t, int P, int Q) { dmma_m8n8k4(acc[t][0], acc[t][1], fr[P], fr[Q]); });
                 }
                 __syncwarp();
                 if (tr_on) trp[2] = clock64();
@@ -769,15 +759,11 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     double *sums = img + (size_t)WS_S * MPAD * MPAD;
     if (warp < WS_S) {
         double *mine = img + (size_t)warp * MPAD * MPAD;
-        int t = 0;
-#pragma unroll
-        for (int P = 0; P < NB; ++P)
-#pragma unroll
-            for (int Q = P; Q < NB; ++Q, ++t) {
-                const int row = 8 * P + (lane >> 2), col = 8 * Q + 2 * (lane & 3);   // C fragment: (lane/4, 2*(lane%4)+{0,1})
-                mine[row * MPAD + col] = acc[t][0];
-                mine[row * MPAD + col + 1] = acc[t][1];
-            }
+        for_each_tile<NB, HB, PM>([&](int t, int P, int Q) {
+            const int row = 8 * P + (lane >> 2), col = 8 * Q + 2 * (lane & 3);   // C fragment: (lane/4, 2*(lane%4)+{0,1})
+            mine[row * MPAD + col] = acc[t][0];
+            mine[row * MPAD + col + 1] = acc[t][1];
+        });
     } else {
         sA = warp_sum(sA); qA = warp_sum(qA); sB = warp_sum(sB); qB = warp_sum(qB);
         if (lane == 0) {
@@ -791,7 +777,8 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     for (int e = threadIdx.x; e < MPAD * MPAD; e += blockDim.x) {
         const int row = e / MPAD, col = e % MPAD;
         double v = 0.0;
-        if (row / 8 <= col / 8) {
+        const bool computed = row / 8 <= col / 8 && (!PM || (row / 8) / HB == (col / 8) / HB);
+        if (computed) {
 #pragma unroll
             for (int w = 0; w < WS_S; ++w) v += img[(size_t)w * MPAD * MPAD + e];
         }
@@ -831,6 +818,42 @@ static __global__ void __launch_bounds__(256) dense_scatter_kernel(int m, int mp
     const int p = e / mpad, q = e % mpad;
     if (p >= m || q >= m || p > q) return;
     partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = sum_over_blocks(blockpart + e, per_block, nblocks);
+}
+
+// CTA partials of the paired layout (fused_wsd_kernel with wsd_paired: Grams of w = (P, A, B) and u = (M, A, B), HS coordinates
+// each) -> packed partial-sum vector of v = (A, B, J_0.., N_0..), CTA order.  First-order entries are exact recombinations
+// (A.J_j = (A.P_j - A.M_j)/2, A.N_j = (A.P_j + A.M_j)/2); the J/N blocks come out symmetrised:
+//   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2,   G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
+// which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).
+static __global__ void __launch_bounds__(256) pm_scatter_kernel(int K, int HS, int nblocks, const double *__restrict__ blockpart,
+                                                                double *__restrict__ partials) {
+    const int mpad = 2 * HS, m = 2 + 2 * K;
+    const size_t per_block = (size_t)mpad * mpad + 4;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < 4) partials[e] = sum_over_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
+    if (e >= m * (m + 1) / 2) return;
+    int p = 0, rowlen = m, rem = e;
+    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
+    const int q = p + rem;
+    auto D = [&](int x, int y) {                               // CTA sum of dense entry (min, max)
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        return sum_over_blocks(blockpart + (size_t)lo * mpad + hi, per_block, nblocks);
+    };
+    double v;
+    if (q < 2) {
+        v = D(K + p, K + q);                                    // A.A, A.B, B.B (w triangle)
+    } else if (p < 2) {
+        const bool qn = q >= 2 + K;
+        const int j = qn ? q - 2 - K : q - 2;
+        const double ap = D(j, K + p), am = D(HS + j, HS + K + p);
+        v = 0.5 * (qn ? ap + am : ap - am);
+    } else {
+        const bool pn = p >= 2 + K, qn = q >= 2 + K;
+        const int i = pn ? p - 2 - K : p - 2, j = qn ? q - 2 - K : q - 2;
+        const double pp = D(i, j), mm = D(HS + i, HS + j);
+        v = 0.25 * (pn == qn ? pp + mm : pp - mm);
+    }
+    partials[4 + e] = v;
 }
 
 // f(M_1[0]): the common shift for the variance sums (identical on every rank).
@@ -873,7 +896,8 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     if (const char *ev = getenv("VS_FUSED_VARIANT")) variant = SECOND ? atoi(ev) : 1;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
-            constexpr int NBk = (M + 7) / 8, MPADk = NBk * 8;
+            constexpr bool PMk = wsd_paired<K, F, SEPARABLE>();
+            constexpr int NBk = PMk ? 2 * pm_hb<K>() : (M + 7) / 8, MPADk = NBk * 8;
             const int eps = variant == 6 ? 3 : 2;
             uint64_t wantd = (nbatch + eps * WS_S - 1) / (eps * WS_S);
             int gridd = (int)(wantd < (uint64_t)c->sm_count ? wantd : (uint64_t)c->sm_count);
@@ -910,8 +934,11 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             }
             const int plen = (int)vs_partials_len(K, 1);
             VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
-            dense_scatter_kernel<<<(MPADk * MPADk + 255) / 256, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
-                                                                                   partials);
+            if constexpr (PMk)
+                pm_scatter_kernel<<<(M * (M + 1) / 2 + 255) / 256, 256, 0, c->stream>>>(K, MPADk / 2, gridd, (const double *)c->block_buf.p, partials);
+            else
+                dense_scatter_kernel<<<(MPADk * MPADk + 255) / 256, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
+                                                                                       partials);
             c->launches++;
             VS_CUDA(cudaGetLastError());
             return VS_OK;
@@ -961,7 +988,7 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
     fc.small_index = 0;
     fc.trace = nullptr;
     fc.alternate = getenv("VS_ALTERNATE") ? atoi(getenv("VS_ALTERNATE")) : 0;
-    fc.rotate = getenv("VS_ROTATE") ? atoi(getenv("VS_ROTATE")) : 0;
+    fc.rotate = 0;
     if (getenv("VS_TRACE")) {
         VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
         VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));
