@@ -348,7 +348,7 @@ def run_gpu(args, rank, world):
         "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA + DMMA share one 36-37 TFLOP/s datapath on B200)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel (ncu --set full at n=2^22: 16.94 MB read, 0 written
                      # = the uint32 permutation; profiles/r01_fused_v3_wsd_ncu_summary.txt), scaled to this rank's rows
-                     "traffic": 16.942592e6 * rows_rank0 / float(1 << 22), "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, 3, 1> (12 E-warps + 4 S-warps per SM, DMMA Gram)", "kernel_ms": kms,
+                     "traffic": 16.942592e6 * rows_rank0 / float(1 << 22), "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, 2, 1> (8 E-warps + 4 S-warps per SM, paired-layout DMMA Gram)", "kernel_ms": kms,
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "DFMA-chain microbenchmark run in this process (vs_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"},
         "clocks": clocks,

@@ -1,3 +1,5 @@
+"""One vs_partials_from_values launch on resident random values (for ncu --set full; not a benchmark).
+usage: python tools/gram_one.py <k> <log2 rows>"""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from varsens_b200 import Context

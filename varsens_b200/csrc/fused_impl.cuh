@@ -46,7 +46,6 @@ struct FusedConst {            // kernel parameter -> constant bank; indexed wit
     uint32_t ndc[K];           // digit rows the cached global table holds per dimension (layout: toff)
     int small_index;           // every Halton index of the run is < 2^29
     int alternate;             // (EPS == 2) E-warp teams alternate generate / evaluate phases -- measured slower, off
-    int rotate;                // (EPS == 3) rotating generate / evaluate / evaluate schedule (see fused_wsd_kernel)
     long long *trace;          // profiling only (VS_TRACE): per-warp clock stamps of CTA 0, else nullptr
     int scale_kind;
     int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
@@ -673,14 +672,14 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         // a warp that generates while the others evaluate finds the LSU free, finishes early and catches up -- and
         // then the two phases add up (clock stamps: 12.6k + 10.5k cycles per batch).  A named barrier over the E-warps
         // after every phase pins team 0 to "generate" while team 1 "evaluates" and vice versa.
-        constexpr bool rotated = false;      // (a barrier-pinned generate/evaluate/evaluate rotation was measured at 6.08 ms vs 5.23 and removed)
+        // (a barrier-pinned generate/evaluate/evaluate rotation of the three E-warps was measured at 6.08 ms vs 5.23 and removed)
         const bool alternate = (EPS == 2) && fc.alternate;
         auto ebar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(WS_E * 32) : "memory"); };
         const int team = e / WS_S;
         const uint64_t bars_total = 2 * count_of(0) + 1;              // count_of(0) is the largest batch count in the CTA
         uint64_t bars_done = 0;
         if (alternate && team == 1) { ebar(); ++bars_done; }
-        for (uint64_t it = 0; !rotated && it < cnt; ++it, bt += G) {
+        for (uint64_t it = 0; it < cnt; ++it, bt += G) {
             const int slot = (int)(it % NBUF);
             double a[K], b[K];
             bool valid = bt * 32 + lane < rows;
@@ -891,8 +890,10 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     const uint64_t nbatch = (rows + 31) / 32;
     // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
     //   1 = single-role warps, register-tile Gram (also the first-order-only kernel)
-    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp (default)
-    int variant = SECOND ? 6 : 1;
+    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp
+    // default: 6, except k >= 20 where the 12-warp form (168 registers per thread, no spills) wins since the paired layout
+    // lightened the S-warps (n = 2^24: 4.79 vs 5.06 ms; k <= 18: variant 6 is 1-13 % faster, tools/variant_sweep.py)
+    int variant = SECOND ? (K >= 20 ? 5 : 6) : 1;
     if (const char *ev = getenv("VS_FUSED_VARIANT")) variant = SECOND ? atoi(ev) : 1;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
@@ -988,7 +989,6 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
     fc.small_index = 0;
     fc.trace = nullptr;
     fc.alternate = getenv("VS_ALTERNATE") ? atoi(getenv("VS_ALTERNATE")) : 0;
-    fc.rotate = 0;
     if (getenv("VS_TRACE")) {
         VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
         VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));
