@@ -790,53 +790,59 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     }
 }
 
-// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector, CTA order.
-// Sum of one entry over all CTA partials, in CTA order (bit-reproducible); the loads of 8 CTAs are issued together so the
-// ~150 L2 round trips of a thread overlap instead of queueing behind each other.
-__device__ __forceinline__ double sum_over_blocks(const double *__restrict__ p, size_t stride, int nblocks) {
+// Sum of one entry over the CTA partials by a whole warp: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree
+// (bit-reproducible for a given grid size; every lane returns the total).  The thread-per-entry form of these scatter
+// kernels took 30-50 us -- a serial chain of 148 strided loads per thread -- which is 5 % of an 8-GPU step.
+__device__ __forceinline__ double warp_sum_over_blocks(const double *__restrict__ p, size_t stride, int nblocks, int lane) {
     double s = 0.0;
-    int b = 0;
-    for (; b + 8 <= nblocks; b += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(b + u) * stride];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-    }
-    for (; b < nblocks; ++b) s += p[(size_t)b * stride];
-    return s;
+    for (int b = lane; b < nblocks; b += 32) s += p[(size_t)b * stride];
+    return warp_sum(s);
 }
 
-// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector, CTA order.
+// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector.  One warp per entry.
 static __global__ void __launch_bounds__(256) dense_scatter_kernel(int m, int mpad, int nblocks, const double *__restrict__ blockpart,
                                                                    double *__restrict__ partials) {
     const size_t per_block = (size_t)mpad * mpad + 4;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < 4) partials[e] = sum_over_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
-    if (e >= mpad * mpad) return;
-    const int p = e / mpad, q = e % mpad;
-    if (p >= m || q >= m || p > q) return;
-    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = sum_over_blocks(blockpart + e, per_block, nblocks);
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w < 4) {
+        const double v = warp_sum_over_blocks(blockpart + (size_t)mpad * mpad + w, per_block, nblocks, lane);
+        if (lane == 0) partials[w] = v;
+        return;
+    }
+    const int e = w - 4;
+    if (e >= m * (m + 1) / 2) return;
+    int p = 0, rowlen = m, rem = e;
+    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
+    const int q = p + rem;
+    const double v = warp_sum_over_blocks(blockpart + (size_t)p * mpad + q, per_block, nblocks, lane);
+    if (lane == 0) partials[4 + e] = v;
 }
 
 // CTA partials of the paired layout (fused_wsd_kernel with wsd_paired: Grams of w = (P, A, B) and u = (M, A, B), HS coordinates
-// each) -> packed partial-sum vector of v = (A, B, J_0.., N_0..), CTA order.  First-order entries are exact recombinations
+// each) -> packed partial-sum vector of v = (A, B, J_0.., N_0..).  First-order entries are exact recombinations
 // (A.J_j = (A.P_j - A.M_j)/2, A.N_j = (A.P_j + A.M_j)/2); the J/N blocks come out symmetrised:
 //   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2,   G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
-// which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).
+// which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).  One warp per entry.
 static __global__ void __launch_bounds__(256) pm_scatter_kernel(int K, int HS, int nblocks, const double *__restrict__ blockpart,
                                                                 double *__restrict__ partials) {
     const int mpad = 2 * HS, m = 2 + 2 * K;
     const size_t per_block = (size_t)mpad * mpad + 4;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < 4) partials[e] = sum_over_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w < 4) {
+        const double v = warp_sum_over_blocks(blockpart + (size_t)mpad * mpad + w, per_block, nblocks, lane);
+        if (lane == 0) partials[w] = v;
+        return;
+    }
+    const int e = w - 4;
     if (e >= m * (m + 1) / 2) return;
     int p = 0, rowlen = m, rem = e;
     while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
     const int q = p + rem;
     auto D = [&](int x, int y) {                               // CTA sum of dense entry (min, max)
         const int lo = x < y ? x : y, hi = x < y ? y : x;
-        return sum_over_blocks(blockpart + (size_t)lo * mpad + hi, per_block, nblocks);
+        return warp_sum_over_blocks(blockpart + (size_t)lo * mpad + hi, per_block, nblocks, lane);
     };
     double v;
     if (q < 2) {
@@ -852,7 +858,7 @@ static __global__ void __launch_bounds__(256) pm_scatter_kernel(int K, int HS, i
         const double pp = D(i, j), mm = D(HS + i, HS + j);
         v = 0.25 * (pn == qn ? pp + mm : pp - mm);
     }
-    partials[4 + e] = v;
+    if (lane == 0) partials[4 + e] = v;
 }
 
 // f(M_1[0]): the common shift for the variance sums (identical on every rank).
@@ -936,9 +942,9 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             const int plen = (int)vs_partials_len(K, 1);
             VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
             if constexpr (PMk)
-                pm_scatter_kernel<<<(M * (M + 1) / 2 + 255) / 256, 256, 0, c->stream>>>(K, MPADk / 2, gridd, (const double *)c->block_buf.p, partials);
+                pm_scatter_kernel<<<(M * (M + 1) / 2 + 4 + 7) / 8, 256, 0, c->stream>>>(K, MPADk / 2, gridd, (const double *)c->block_buf.p, partials);
             else
-                dense_scatter_kernel<<<(MPADk * MPADk + 255) / 256, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
+                dense_scatter_kernel<<<(M * (M + 1) / 2 + 4 + 7) / 8, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
                                                                                        partials);
             c->launches++;
             VS_CUDA(cudaGetLastError());

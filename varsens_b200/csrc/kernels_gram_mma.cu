@@ -288,30 +288,35 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
     }
 }
 
-static __device__ __forceinline__ double sum_blocks(const double *__restrict__ p, size_t stride, int nblocks) {
-    double s = 0.0;
-    int b = 0;
-    for (; b + 8 <= nblocks; b += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(b + u) * stride];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-    }
-    for (; b < nblocks; ++b) s += p[(size_t)b * stride];
-    return s;
-}
-
-// per-CTA dense images (mpad x mpad + 4 sums) -> packed partial-sum vector, CTA order; entries that were not computed are 0
+// per-CTA dense images (mpad x mpad + 4 sums) -> packed partial-sum vector; entries that were not computed are 0.
+// One warp per entry: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree (reproducible for a given grid).
 __global__ void __launch_bounds__(256) gram_mma_scatter_kernel(int m, int mpad, int pmax, int nblocks, const double *__restrict__ blockpart,
                                                                double *__restrict__ partials) {
     const size_t per_block = (size_t)mpad * mpad + 4;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < 4) partials[e] = sum_blocks(blockpart + (size_t)mpad * mpad + e, per_block, nblocks);
-    if (e >= mpad * mpad) return;
-    const int p = e / mpad, q = e - p * mpad;
-    if (p >= m || q >= m || p > q) return;
-    partials[4 + (size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)] = p < pmax ? sum_blocks(blockpart + e, per_block, nblocks) : 0.0;
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nent = (long long)m * (m + 1) / 2;
+    if (w >= nent + 4) return;
+    const double *src;
+    long long dst;
+    bool computed = true;
+    if (w < 4) {
+        src = blockpart + (size_t)mpad * mpad + w;
+        dst = w;
+    } else {
+        long long rem = w - 4;
+        int p = 0, rowlen = m;
+        while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
+        const int q = p + (int)rem;
+        src = blockpart + (size_t)p * mpad + q;
+        dst = w;
+        computed = p < pmax;
+    }
+    double s = 0.0;
+    if (computed)
+        for (int b = lane; b < nblocks; b += 32) s += src[(size_t)b * per_block];
+    s = warp_sum(s);
+    if (lane == 0) partials[dst] = s;
 }
 
 template <int ST, bool MULTI, bool GUARD>
@@ -334,7 +339,7 @@ static int launch_mma_t(vs_ctx *c, const MmaGeom &g, size_t smem, uint64_t rows,
     time_end(c);
     c->launches++;
     VS_CUDA(cudaGetLastError());
-    gram_mma_scatter_kernel<<<(g.mpad * g.mpad + 255) / 256, 256, 0, c->stream>>>(g.m, g.mpad, g.second ? g.m : 8, gx,
+    gram_mma_scatter_kernel<<<(unsigned)(((size_t)g.m * (g.m + 1) / 2 + 4 + 7) / 8), 256, 0, c->stream>>>(g.m, g.mpad, g.second ? g.m : 8, gx,
                                                                                  (const double *)c->block_buf.p, partials);
     c->launches++;
     VS_CUDA(cudaGetLastError());
