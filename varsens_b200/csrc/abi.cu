@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) sum_chunks_kernel(int plen, int nchunk, c
 }
 
 // Host permutation + fused kernel: the H2D copy of the permutation (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over
-// PCIe) is cut into chunks on the copy stream and the fused kernel is launched per chunk as its slice arrives, so only the
+// PCIe) is cut into 2-4 growing slices on the copy stream and the fused kernel is launched per chunk as its slice arrives, so only the
 // first slice is exposed.  Chunk partial sums are added in chunk order.  (vs_run_fused / vs_fused_partials with VS_MEM_HOST.)
 static const uint64_t PIPE_MIN_ROWS = 1ull << 21;
 
@@ -249,8 +249,11 @@ static int fused_partials_pipelined(vs_ctx *c, int k, uint64_t n, uint64_t disca
                                     int objective, const double *params, int n_params, uint64_t i_begin, uint64_t i_end, int flags,
                                     double *partials_dev) {
     const uint64_t rows = i_end - i_begin;
+    // Slices grow: the first one is small so that little of the copy is exposed, the later ones are large so that few
+    // kernel start-ups and tails are paid (at k = 20 a slice computes ~4x longer than it copies).  Sixteenths of the rows.
+    static const int cuts[5][5] = {{0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};
     int nchunk = (int)(rows >> 20);
-    if (nchunk > 8) nchunk = 8;
+    if (nchunk > 4) nchunk = 4;
     const size_t plen = vs_partials_len(k, 1);
     VS_TRY(ensure(c, c->perm_buf, rows * sizeof(uint32_t)));
     VS_TRY(ensure(c, c->pipe_buf, (size_t)nchunk * plen * sizeof(double)));
@@ -269,7 +272,7 @@ static int fused_partials_pipelined(vs_ctx *c, int k, uint64_t n, uint64_t disca
     // the copies may not overwrite the staging buffer before earlier work on the compute stream has finished reading it
     VS_CUDA(cudaEventRecord(c->pipe_ev[nchunk], c->stream));
     VS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[nchunk], 0));
-    auto bound = [&](int ch) { return i_begin + rows * (uint64_t)ch / (uint64_t)nchunk; };
+    auto bound = [&](int ch) { return i_begin + rows / 16 * (uint64_t)cuts[nchunk][ch] + (ch == nchunk ? rows % 16 : 0); };
     for (int ch = 0; ch < nchunk; ++ch) {
         const uint64_t b = bound(ch), e = bound(ch + 1);
         VS_CUDA(cudaMemcpyAsync((uint32_t *)c->perm_buf.p + (b - i_begin), perm_host + b, (e - b) * sizeof(uint32_t),
