@@ -59,13 +59,15 @@ __device__ __forceinline__ double source_b(const SourceDev &src, int k, uint64_t
 struct GFunction {
     const double *inv;   // 1/(1+a_c)
     const double *off;   // a_c/(1+a_c)
+    static constexpr bool product_form = true;           // f(x) = prod_c term(c, x_c), evaluated in ascending c from 1.0
+    __device__ __forceinline__ double term(int c, double x) const {
+        double t = fma(4.0, x, -2.0);                     // 4x - 2         (2 flops)
+        return fma(fabs(t), inv[c], off[c]);              // (|t| + a)/(1+a) (2)
+    }
     template <class X>
     __device__ __forceinline__ double operator()(const X &x, int k) const {
         double p = 1.0;
-        for (int c = 0; c < k; ++c) {
-            double t = fma(4.0, x[c], -2.0);            // 4x - 2         (2 flops)
-            p *= fma(fabs(t), inv[c], off[c]);          // (|t| + a)/(1+a) (2) ; running product (1)
-        }
+        for (int c = 0; c < k; ++c) p *= term(c, x[c]);   // running product (1)
         return p;
     }
 };

@@ -1,6 +1,8 @@
 // Objective evaluation to HBM (two-phase path), Gram/partial-sum reduction of given values, finalisation.
 #include "device.cuh"
 
+#include <type_traits>
+
 namespace vs {
 
 // ---------------------------------------------------------------------------------------------
@@ -16,6 +18,9 @@ struct SmemPoint {
     int j, stride;
     __device__ __forceinline__ double operator[](int c) const { return (c == j ? other : base)[c * stride]; }
 };
+
+template <class F, class = void> struct has_product_form : std::false_type {};
+template <class F> struct has_product_form<F, std::enable_if_t<F::product_form>> : std::true_type {};
 
 template <class F>
 __global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end,
@@ -36,14 +41,42 @@ __global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, Scal
     const int npts = 2 + 2 * k;
     int p0 = blockIdx.y * pts_per_chunk, p1 = p0 + pts_per_chunk;
     if (p1 > npts) p1 = npts;
-    for (int p = p0; p < p1; ++p) {
-        SmemPoint x;
-        x.stride = nthr;
-        if (p == 0) { x.base = A; x.other = A; x.j = -1; }
-        else if (p == 1) { x.base = B; x.other = B; x.j = -1; }
-        else if (p < 2 + k) { x.base = B; x.other = A; x.j = p - 2; }          // N_j[j]  : M_2 with col j from M_1
-        else { x.base = A; x.other = B; x.j = p - 2 - k; }                      // N_nj[j] : M_1 with col j from M_2
-        fvals[(uint64_t)p * rows + r] = f(x, k);
+    if constexpr (has_product_form<F>::value) {
+        // Product-form functors: six design points advance together, coordinate by coordinate.  They share the two
+        // shared-memory reads of (A_c, B_c) and the functor's parameter reads, and give six independent product chains
+        // (one point at a time is latency- and LSU-bound: ~9 warps per SM fit next to the staged rows at k = 50).
+        // Same operations in the same order per point as F::operator().
+        constexpr int NPB = 6;
+        for (int p = p0; p < p1; p += NPB) {
+            double pr[NPB];
+            int jj[NPB];
+            bool base_a[NPB];
+#pragma unroll
+            for (int u = 0; u < NPB; ++u) {
+                const int P = p + u < p1 ? p + u : p1 - 1;
+                pr[u] = 1.0;
+                base_a[u] = (P == 0) || (P >= 2 + k);                     // M_1 or N_nj[j] (M_1 with column j from M_2)
+                jj[u] = P < 2 ? -1 : (P < 2 + k ? P - 2 : P - 2 - k);
+            }
+            for (int c = 0; c < k; ++c) {
+                const double ac = A[c * nthr], bc = B[c * nthr];
+#pragma unroll
+                for (int u = 0; u < NPB; ++u) pr[u] *= f.term(c, (base_a[u] != (c == jj[u])) ? ac : bc);
+            }
+#pragma unroll
+            for (int u = 0; u < NPB; ++u)
+                if (p + u < p1) fvals[(uint64_t)(p + u) * rows + r] = pr[u];
+        }
+    } else {
+        for (int p = p0; p < p1; ++p) {
+            SmemPoint x;
+            x.stride = nthr;
+            if (p == 0) { x.base = A; x.other = A; x.j = -1; }
+            else if (p == 1) { x.base = B; x.other = B; x.j = -1; }
+            else if (p < 2 + k) { x.base = B; x.other = A; x.j = p - 2; }          // N_j[j]  : M_2 with col j from M_1
+            else { x.base = A; x.other = B; x.j = p - 2 - k; }                      // N_nj[j] : M_1 with col j from M_2
+            fvals[(uint64_t)p * rows + r] = f(x, k);
+        }
     }
 }
 
