@@ -378,6 +378,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
             const double cost = passes * (mma > copy ? mma : copy);
             if (nunits <= 128 && (best == 0.0 || cost < best)) { best = cost; ST = st; }
         }
+        if (best == 0.0) return VS_OK;            // more super-tiles than the tables hold: register-tile kernel
     }
     if (const char *ev = getenv("VS_GRAM_ST")) { int v = atoi(ev); if (multi && (v == 2 || v == 4)) ST = v; }      // tuning switch
     const bool guard = multi || !g.second || g.nb != ST;
