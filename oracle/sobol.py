@@ -15,8 +15,8 @@ significant digits (default ostream precision, sobolGen.cpp:59).
 
 Direction integers: Joe-Kuo (new-joe-kuo-6.21201) built from scipy's bundled table, the only
 table available offline; the logic is pinned bit-exactly against
-scipy.stats.qmc.Sobol(scramble=False, bits=32) in tests/test_oracle_sobol.py and the golden
-fixture tests/golden/sobol_joekuo.npz.
+scipy.stats.qmc.Sobol(scramble=False, bits=32) in tests/test_oracle_reference_parity.py
+(test_sobol_against_scipy_fixture) and the golden fixture tests/golden/golden.npz.
 """
 import os
 
