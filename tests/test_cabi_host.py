@@ -211,3 +211,31 @@ def test_reference_permutation_cache_keeps_rng_side_effect():
     for n in range(10, 20):                                      # bounded: only the newest few are kept
         vsalt._reference_permutation(n)
     assert len(vsalt._perm_cache) <= 4
+
+
+def test_header_enums_match_python_binding():
+    """The ctypes binding hard-codes the header's enum values: parse include/varsens_b200.h and compare."""
+    from varsens_b200 import _cabi
+    text = open(os.path.join(ROOT, "include", "varsens_b200.h")).read()
+    vals = {}
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for body in re.findall(r"enum\s*\w*\s*\{([^}]*)\}", text):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, v = [t.strip() for t in item.split("=")]
+                nxt = int(v, 0)
+            else:
+                name = item
+            vals[name] = nxt
+            nxt += 1
+    want = {"VS_MEM_HOST": _cabi.MEM_HOST, "VS_MEM_DEVICE": _cabi.MEM_DEVICE, "VS_SCALE_IDENTITY": _cabi.SCALE_IDENTITY,
+            "VS_SCALE_LINEAR": _cabi.SCALE_LINEAR, "VS_SCALE_POWER": _cabi.SCALE_POWER, "VS_OBJ_GFUNCTION": _cabi.OBJ_GFUNCTION,
+            "VS_OBJ_ISHIGAMI": _cabi.OBJ_ISHIGAMI, "VS_OBJ_RK4_CHAIN": _cabi.OBJ_RK4_CHAIN,
+            "VS_FLAG_SECOND_ORDER": _cabi.FLAG_SECOND_ORDER, "VS_FLAG_SEPARABLE": _cabi.FLAG_SEPARABLE, "VS_OK": 0}
+    for name, v in want.items():
+        assert vals.get(name) == v, (name, vals.get(name), v)
+    assert cport.OBJ_GFUNCTION == _cabi.OBJ_GFUNCTION and cport.OBJ_RK4_CHAIN == _cabi.OBJ_RK4_CHAIN     # oracle ids follow the ABI
