@@ -293,7 +293,8 @@ extern "C" int vs_ctx_destroy(vs_ctx *c) {
     if (!c) return VS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->peer_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
+    cudaStreamSynchronize(c->copy_stream);
+    DevBuf *bufs[] = {&c->peer_buf, &c->pipe_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
                       &c->part_buf,  &c->block_buf, &c->res_buf, &c->dir_buf, &c->misc_buf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
