@@ -175,8 +175,7 @@ def run_gpu(args, rank, world):
     import torch
     import torch.distributed as dist
     import varsens_b200 as vb
-    from varsens_b200 import _cabi, dist as vdist
-    from oracle import pipeline
+    from varsens_b200 import _cabi, dist as vdist, saltelli as vsalt
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -184,79 +183,58 @@ def run_gpu(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = vb.Context.get(local)
-    work_stream = torch.cuda.Stream(device=dev)                   # graph capture needs a non-default stream
+    work_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(work_stream)
     ctx.set_stream(work_stream.cuda_stream)
 
     n, k = N_ROWS, K
     flags = _cabi.FLAG_SECOND_ORDER
-    perm_host = torch.from_numpy(pipeline.permutation(n).astype(numpy.int32)).pin_memory()   # reference's own RNG, saltelli.py:100-101
+    t0 = time.perf_counter()
+    perm_np = vsalt._reference_permutation(n)                     # the reference's own RNG call (saltelli.py:100-101), product code
+    perm_draw_s = time.perf_counter() - t0
+    perm_host = torch.from_numpy(perm_np.astype(numpy.int32)).pin_memory()
     perm_dev = perm_host.to(dev)
     lo, hi = vdist.shard_range(n, rank, world)
     plen = vdist.partials_layout(k)["length"]
     part = torch.zeros(plen, dtype=torch.float64, device=dev)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    ex = None
+    if world > 1 and not vdist.use_nccl():
+        ex = vdist.peer_exchange(plen, dev)                             # symmetric memory over NVLink; None -> NCCL
+    exchange = "none" if world == 1 else ("one-launch step: peer-memory all-reduce over NVLink inside the fused kernel" if ex is not None
+                                          else "NCCL all_reduce between vs_fused_partials and vs_finalize")
 
-    res_dev = torch.empty(_cabi.Result.flat_len(k, 1), dtype=torch.float64, device=dev)
-
-    def body_resident():
-        ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-        if world > 1:
-            vdist.allreduce_partials(part)                            # one NCCL all-reduce of the partial sums
-        ctx.finalize_device(k, 1, n, part, res_dev, flags)
-
-    # Optional (VS_BENCH_GRAPH=1, single GPU): capture the resident step (shift + fused kernel + scatter + finalize) once in
-    # a CUDA graph and replay it; saves ~0.07 ms of launch/Python time per step.  Off by default so that every N runs the
-    # same eager path.
-    graph = None
-    mode = "eager"
-    launches_per_step = None
-    if os.environ.get("VS_BENCH_GRAPH", "0") == "1" and world == 1:      # opt-in; capturing the NCCL all-reduce hung at N=2 (r01)
-        try:
-            for _ in range(2):
-                body_resident()
-            torch.cuda.synchronize()
-            c0 = ctx.launch_count()
-            body_resident()
-            launches_per_step = ctx.launch_count() - c0                  # our kernels per step (replays do not pass the counter)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=torch.cuda.current_stream(), capture_error_mode="thread_local"):
-                body_resident()
-            mode = "cuda graph"
-        except Exception as exc:                                          # capture not possible: run the same calls eagerly
-            graph = None
-            mode = "eager (graph capture failed: %s)" % (str(exc).splitlines()[0][:80],)
-            torch.cuda.synchronize()
+    def step_with(perm, use_ex):
+        """One step = indices of the full design on the host.  N=1: vs_run_fused (one launch).  N>1: vs_run_fused_p2p (one launch
+        per rank, exchange inside the kernel) or, NCCL arm, vs_fused_partials -> all_reduce -> vs_finalize."""
+        if world == 1:
+            return ctx.run_fused(k, n, perm, _cabi.OBJ_GFUNCTION, A, flags=flags)
+        if use_ex is not None:
+            return ctx.run_fused_p2p(k, n, perm, _cabi.OBJ_GFUNCTION, A, use_ex.world, use_ex.rank, use_ex.peer_bufs, use_ex.peer_flags,
+                                     use_ex.next_epoch(), lo, hi, flags=flags)
+        ctx.fused_partials(k, n, perm, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
+        vdist.allreduce_partials(part)                                  # same stream as the ctx (set_stream above)
+        return ctx.finalize(k, 1, n, part, flags)
 
     def step_resident():
-        if graph is not None:
-            graph.replay()
-            return _cabi.Result.from_flat(k, 1, res_dev.cpu().numpy())    # D2H of the indices + sync, inside the timed region
-        if world > 1 and os.environ.get("VS_P2P", "0") == "1":
-            ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-            return vdist.reduce_and_finalize(ctx, k, n, part, flags)     # fused peer-memory all-reduce + finalize kernel
-        body_resident()
-        return _cabi.Result.from_flat(k, 1, res_dev.cpu().numpy())
+        return step_with(perm_dev, ex)
 
     def step_e2e():
-        # public call with HOST buffers: permutation slice H2D from pinned memory, indices D2H, every step
-        if world == 1:
-            return ctx.run_fused(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, flags=flags)
-        ctx.fused_partials(k, n, perm_host, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-        return vdist.reduce_and_finalize(ctx, k, n, part, flags)
+        # public call with HOST buffers: permutation slice H2D from pinned memory, indices to the host, every step
+        return step_with(perm_host, ex)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, kernel_ms=None):
+    def timed(fn, steps, warmup, kernel_ms=None, wall_too=False):
         for _ in range(warmup):
             fn()
             flush.zero_()
         barrier()
         tot = 0.0
+        res = None
         for _ in range(steps):
             flush.zero_()                                               # L2 flush between timed iterations
             torch.cuda.synchronize()
@@ -271,8 +249,8 @@ def run_gpu(args, rank, world):
             torch.cuda.synchronize()
             wall = (time.perf_counter() - t0) * 1e3
             dev_ms = e0.elapsed_time(e1)
-            tot += max(dev_ms, wall) if fn is step_e2e else dev_ms      # e2e includes the host-side call/return
-            if kernel_ms is not None and graph is None:
+            tot += max(dev_ms, wall) if wall_too else dev_ms            # e2e includes the host-side call/return
+            if kernel_ms is not None:
                 kernel_ms.append(ctx.last_kernel_ms())
         barrier()
         t = torch.tensor([tot / steps], dtype=torch.float64, device=dev)
@@ -286,18 +264,22 @@ def run_gpu(args, rank, world):
     kernel_ms = []
     ms, res = timed(step_resident, args.steps, args.warmup, kernel_ms)
     launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
-    if graph is not None:
-        launches = launches_per_step * args.steps
-    ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3))
+    tail_ns = ctx.last_tail_ns(k).tolist()
+    ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3), wall_too=True)
     clocks = sampler.stop() if sampler else None          # sampled over both timed regions
 
-    # index time: from "partial sums of every rank ready" to the indices on the host = all-reduce + finalize +
-    # D2H; and, single GPU, from "all 2n(1+k) values resident" to the indices on the host (vs_indices_from_values path).
+    # the other exchange, for the record (N>1): NCCL all_reduce between the partial-sum launch and the finalize launch
+    nccl_ms = None
+    if world > 1 and ex is not None:
+        nccl_ms, res_nccl = timed(lambda: step_with(perm_dev, None), max(3, args.steps // 2), 3)
+        nccl_same = bool(numpy.allclose(res_nccl.sens, res.sens, rtol=1e-12, atol=1e-14))
+
+    # index time: from "partial sums of every rank ready" to the indices on the host
     def step_index():
         if world > 1:
             vdist.allreduce_partials(part)
-        ctx.finalize_device(k, 1, n, part, res_dev, flags)
-        return _cabi.Result.from_flat(k, 1, res_dev.cpu().numpy())
+        return ctx.finalize(k, 1, n, part, flags)
+    ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
     part_keep = part.clone()
     index_ms, _ = timed(step_index, args.steps, 3)
     part.copy_(part_keep)
@@ -310,56 +292,81 @@ def run_gpu(args, rank, world):
         except Exception as exc:                                                         # extra figure only; never fail the bench on it
             index_values_ms = "failed: %s" % (str(exc).splitlines()[0][:80],)
 
-    # fused kernel alone (this rank's shard), separable shortcut for context
-    sep_ms = None
+    # separable shortcut for context; the drop-in Python API, first and cached call
+    sep_ms = api_first_ms = api_cached_ms = None
     if world == 1:
         ms_sep, _ = timed(lambda: ctx.run_fused(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A,
                                                 flags=flags | _cabi.FLAG_SEPARABLE), max(2, args.steps // 2), 2)
         sep_ms = ms_sep
+        vsalt._perm_cache.clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v = vb.Varsens(vb.GFunction(A), lambda x: x, k, n, verbose=False)
+        api_first_ms = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        v = vb.Varsens(vb.GFunction(A), lambda x: x, k, n, verbose=False)
+        api_cached_ms = (time.perf_counter() - t0) * 1e3
+        api_same = bool((v.sens == res.sens).all())
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    if graph is not None:                                          # kernel time: a few eager launches of the same shard
-        kernel_ms = []
-        for _ in range(max(3, args.steps // 2)):
-            flush.zero_()
-            ctx.fused_partials(k, n, perm_dev, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-            torch.cuda.synchronize()
-            kernel_ms.append(ctx.last_kernel_ms())
     kms = float(numpy.mean(kernel_ms))
     rows_rank0 = hi - lo
     flops = algorithmic_flops_per_row(k) * rows_rank0
     achieved = flops / (kms * 1e-3) / 1e12
+    executed = (algorithmic_flops_per_row(k) - (2 + 2 * k) * (k - 1)) * rows_rank0 / (kms * 1e-3) / 1e12
+    # DRAM traffic of the fused kernel: from the committed ncu --set full capture of this very variant (tools/ncu_summary.py
+    # writes the json next to the summary); scaled by rows.  null when no capture of this build is committed.
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "r02_fused_k20_traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as fh:
+            t = json.load(fh)
+        traffic = float(t["dram_bytes"]) * rows_rank0 / float(t["rows"])
+        traffic_src = "profiles/%s (ncu --set full, %s, n=%d)" % (t["file"], t["kernel"], t["rows"])
+    variant = "2 E-warps per S-warp (12 warps)" if os.environ.get("VS_FUSED_VARIANT", "") in ("", "0", "5") else "variant %s" % os.environ["VS_FUSED_VARIANT"]
     line = {
         "metric": METRIC, "value": evals(n) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 Sobol g-function k=20 n=2^24 identity scaling, fused generic functor, second order on",
-                   "k": k, "n": n, "evals_per_step": evals(n), "parallelism": "rows sharded over %d rank(s), 1 all-reduce of %d doubles (%s)" % (world, plen, "fused peer-memory kernel over NVLink" if (world > 1 and os.environ.get("VS_P2P", "0") == "1" and vdist.peer_exchange(plen, dev) is not None) else "NCCL" if world > 1 else "none"),
-                   "l2": "192 MiB buffer written between timed iterations (L2 flush)", "index_time_ms": "included (finalize kernel + D2H of %d doubles)" % (6 * k + 2 + 2 * k * k), "resident_step": mode},
-        "index_time": {"partials_to_host_indices_ms": index_ms, "what": "%sfinalize kernel + D2H of the indices, timed alone" % ("NCCL all-reduce of the partial sums + " if world > 1 else ""),
+                   "k": k, "n": n, "evals_per_step": evals(n),
+                   "parallelism": "rows sharded over %d rank(s); exchange of %d doubles: %s" % (world, plen, exchange),
+                   "l2": "192 MiB buffer written between timed iterations (L2 flush)",
+                   "step": "ONE kernel launch per rank: generation + evaluation + Gram + fixed-order combine%s + estimators, results written to mapped host memory" % (" + peer-memory all-reduce" if ex is not None else "") if (world == 1 or ex is not None) else "vs_fused_partials (1 launch) + NCCL all_reduce + finalize kernel"},
+        "index_time": {"partials_to_host_indices_ms": index_ms, "what": "%sfinalize kernel writing to mapped host memory, timed alone" % ("NCCL all-reduce of the partial sums + " if world > 1 else ""),
+                       "in_kernel_tail_ns": {"combine_pack": tail_ns[0], "peer_stores_flags": tail_ns[1], "wait_for_peers": tail_ns[2], "sum_estimators_store": tail_ns[3],
+                                             "what": "globaltimer stamps inside the last CTA of the fused kernel, last resident step, rank 0"},
                        "values_to_host_indices_ms": index_values_ms, "values_what": "vs_indices_from_values on 2n(1+k) = %d resident values (bulk-copy + DMMA Gram kernel)" % evals(n)},
         "e2e": {"value": evals(n) / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k))},
+                "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k)),
+                "how": "host permutation (pinned) copied in slices on a copy stream; the one fused launch polls an arrival counter per slice; indices land in mapped host memory"},
         "gpu_launches": int(launches),
         # "tensor" = compute bound; the pipe is FP64: evaluation on DFMA, Gram on DMMA (mma.sync m8n8k4.f64), which share one datapath
         "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA + DMMA share one 36-37 TFLOP/s datapath on B200)", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel (ncu --set full at n=2^22: 16.94 MB read, 0 written
-                     # = the uint32 permutation; profiles/r01_fused_v3_wsd_ncu_summary.txt), scaled to this rank's rows
-                     "traffic": 16.942592e6 * rows_rank0 / float(1 << 22), "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, 2, 1> (8 E-warps + 4 S-warps per SM, paired-layout DMMA Gram)", "kernel_ms": kms,
+                     "frac_executed": executed / peak_tflops,
+                     "frac_note": "frac credits SURVEY.md 8(d)'s 5k flops per evaluation; the kernel hoists the k divisions by (1+a_c) of a point into one multiply, so frac_executed counts (k-1) fewer flops per evaluation",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "vs::fused_wsd_kernel<20, GFunctionReg<20>, false, EPS, 1> (%s, paired-layout DMMA Gram, in-kernel tail)" % variant, "kernel_ms": kms,
+                     "kernel_ms_note": "CUDA events around the launch inside the library; at N>1 it includes the wait for the slowest peer in the tail",
                      "algorithmic_flops_per_launch": flops,
                      "peak_source": "DFMA-chain microbenchmark run in this process (vs_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"},
         "clocks": clocks,
         "check": {"var_y": float(res.var_y[0]), "E_2": float(res.E_2[0]), "sens0": float(res.sens[0, 0]),
-                  # e2e adds the chunk partial sums of the pipelined H2D path in chunk order: same indices up to summation order
-                  "e2e_matches_resident": bool(numpy.allclose(res.sens, res2.sens, rtol=1e-11, atol=1e-13)),
+                  "e2e_matches_resident_bitwise": bool((res.sens == res2.sens).all() and (res.sens_2 == res2.sens_2).all()),
                   "e2e_max_abs_diff_sens": float(numpy.max(numpy.abs(res.sens - res2.sens)))},
+        "host_permutation": {"draw_s": perm_draw_s, "what": "numpy.random.seed(1); shuffle of n indices (saltelli.py:100-101), once, outside the timed regions"},
     }
+    if nccl_ms is not None:
+        line["nccl_arm"] = {"ms_per_step": nccl_ms, "value": evals(n) / (nccl_ms * 1e-3), "unit": UNIT, "matches_peer_memory_step": nccl_same,
+                            "what": "vs_fused_partials + torch.distributed.all_reduce (NCCL) + vs_finalize, resident permutation"}
     if sep_ms is not None:
         line["separable_shortcut"] = {"value": evals(n) / (sep_ms * 1e-3), "unit": UNIT, "ms_per_step": sep_ms,
                                       "note": "prefix/suffix products (VS_FLAG_SEPARABLE); not used for value/roofline"}
+        line["python_api"] = {"api_first_call_ms": api_first_ms, "api_cached_ms": api_cached_ms, "bitwise_equal_to_c_abi_step": api_same,
+                              "what": "Varsens(GFunction(A), lambda x: x, 20, 2**24): first call draws the seeded permutation on the host, later calls reuse it"}
     if world == 1 and not args.no_cpu:
         v, cores, sample, _ = cpu_numpy_evals_per_s(target_seconds=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -34,7 +34,8 @@ extern "C" {
 
 typedef struct vs_ctx vs_ctx;
 
-enum vs_status { VS_OK = 0, VS_ERR_ARG = 1, VS_ERR_CUDA = 2, VS_ERR_RANGE = 3, VS_ERR_NOMEM = 4, VS_ERR_UNSUPPORTED = 5 };
+enum vs_status { VS_OK = 0, VS_ERR_ARG = 1, VS_ERR_CUDA = 2, VS_ERR_RANGE = 3, VS_ERR_NOMEM = 4, VS_ERR_UNSUPPORTED = 5,
+                 VS_ERR_TIMEOUT = 6 /* a peer rank did not show up in the peer-memory all-reduce */ };
 enum vs_mem { VS_MEM_HOST = 0, VS_MEM_DEVICE = 1 };
 
 /* varsens/scale.py: identity (lambda x: x), linear (:33), power (:62).  percentage (:90-91) lowers
@@ -55,6 +56,17 @@ typedef struct vs_scale {
  *                forward rates x[0..k/2), reverse rates x[k/2..k), X(0) = e_0, classic RK4,
  *                f = X_{k/2}(nsteps*dt)       (spec frozen in oracle/objectives.py) */
 enum vs_objective { VS_OBJ_GFUNCTION = 0, VS_OBJ_ISHIGAMI = 1, VS_OBJ_RK4_CHAIN = 2 };
+
+/* fp64 arithmetic of the Halton radical inverse (the reference delegates it to the third-party ghalton package,
+ * varsens/saltelli.py:82-84, whose source is not part of the reference; see DESIGN.md "parity unpinned").  The first three are
+ * in-order sums of per-digit terms, least significant digit first, and differ only in how a term is rounded:
+ *   DIVIDE               term = digit / b^(j+1)                       (default: ghalton as restated in oracle/halton.py)
+ *   RECIPROCAL           term = digit * (1.0 / b^(j+1))
+ *   RUNNING_RECIPROCAL   term = digit * f_j,  f_0 = 1.0 / b,  f_{j+1} = f_j * (1.0 / b)
+ *   HORNER               x = (x + digit_j) / b from the most significant digit down (no term table: the fused kernels do not
+ *                        run in this mode, the generators / export / two-phase paths do)
+ * Selected per context: VS_HALTON_MODE in the environment at vs_ctx_create, or vs_ctx_set_halton_mode. */
+enum vs_halton_mode { VS_HALTON_DIVIDE = 0, VS_HALTON_RECIPROCAL = 1, VS_HALTON_RUNNING_RECIPROCAL = 2, VS_HALTON_HORNER = 3 };
 
 enum vs_flags {
     VS_FLAG_SECOND_ORDER = 1, /* also accumulate the k x k Grams for sens_2 / sens_2n */
@@ -78,6 +90,11 @@ int vs_ctx_destroy(vs_ctx *ctx);
 /* Run on a caller stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
 int vs_ctx_set_stream(vs_ctx *ctx, void *cuda_stream);
 int vs_ctx_synchronize(vs_ctx *ctx);
+/* Tuning / diagnostic switches (VS_FUSED_VARIANT, VS_NO_PIPELINE, VS_GRAM_*, VS_P2P_TIMEOUT_MS, VS_HALTON_MODE, VS_TRACE ...) are
+ * read from the environment once, at vs_ctx_create -- never on a launch path.  This re-reads them. */
+int vs_ctx_reload_env(vs_ctx *ctx);
+/* Halton arithmetic of this context (enum vs_halton_mode); drops the cached term table. */
+int vs_ctx_set_halton_mode(vs_ctx *ctx, int mode);
 /* Kernels launched by this ctx since creation (bench.py's gpu_launches). */
 uint64_t vs_ctx_launch_count(const vs_ctx *ctx);
 
@@ -90,6 +107,9 @@ int vs_halton_bases(int k, uint32_t *bases);
  * the kernels at a different ghalton build). */
 int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offsets, double *terms,
                     uint64_t capacity, uint64_t *count);
+/* The same table in any of the three term-table modes (enum vs_halton_mode); VS_HALTON_HORNER has no table: VS_ERR_UNSUPPORTED. */
+int vs_halton_terms_mode(int k, uint64_t max_index, int mode, uint32_t *ndigits, uint32_t *offsets, double *terms,
+                         uint64_t capacity, uint64_t *count);
 /* Length of the partial-sum vector for k factors and l outputs: 4l + m(m+1)/2, m = (2+2k) l.
  * Layout: S_A[l], S_B[l], Q_A[l], Q_B[l] (sums / sums of squares of fM_1 - c, fM_2 - c for a
  * common shift c), then the upper triangle (row-major, t <= u) of G[t][u] = sum_i v_i[t] v_i[u]
@@ -177,12 +197,28 @@ int vs_run_fused(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_
                  const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
                  int n_params, int flags, vs_result *result);
 
+/* Multi-GPU form of vs_run_fused: ONE kernel launch per rank and step.  Rank `rank` of `world_size` evaluates base rows
+ * [i_begin,i_end) of the n-row design; the last CTA of its kernel combines the CTA sums in fixed order, stores the packed
+ * partial sums into slot `rank` of every peer's exchange buffer over NVLink (one warp per peer), publishes the epoch flag,
+ * waits -- at most VS_P2P_TIMEOUT_MS (default 10 s), then VS_ERR_TIMEOUT -- for the other ranks, sums the slots in rank
+ * order (identical bits on every rank), computes the estimators and writes them to mapped host memory.  Buffers, flags and
+ * epoch are those of vs_allreduce_finalize_p2p.  There is no NCCL call and no separate reduction, finalisation or copy
+ * launch.  Replaces varsens/saltelli.py:82-125, :308-353, :572-622 and the file-batch gather of :415-472. */
+int vs_run_fused_p2p(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                     const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                     int n_params, uint64_t i_begin, uint64_t i_end, int flags, int world_size, int rank,
+                     const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch, vs_result *result);
+
 /* ---- measurement helpers --------------------------------------------------------------------------- */
 /* DFMA-chain microbenchmark: returns measured FP64 TFLOP/s (FMA = 2 flops) of this GPU in *tflops. */
 int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops);
 /* Device time in ms of the last vs_fused_partials / vs_eval_values / vs_partials_from_values /
  * vs_sample_flat main kernel, from CUDA events recorded on the ctx stream. */
 int vs_last_kernel_ms(vs_ctx *ctx, float *ms);
+/* Time stamps (ns, %globaltimer) of the tail of the last one-launch fused step with estimators (vs_run_fused /
+ * vs_run_fused_p2p, k factors): ns4 = {combine + pack, peer stores + fence + flags, wait for the peers, rank-order sum +
+ * estimators + result stores}. */
+int vs_last_tail_ns(vs_ctx *ctx, int k, double *ns4);
 
 #ifdef __cplusplus
 }

@@ -117,31 +117,40 @@ static double f_ishigami(const double *x, int k, const double *par) {
     return s0 + par[0] * s1 * s1 + par[1] * (x2 * x2) * (x2 * x2) * s0;
 }
 
+/* RK4 mass-action chain, FROZEN ARITHMETIC shared with the device functor (varsens_b200/csrc/device.cuh: RK4Chain):
+ *   flux_s = fma(kf_s, X_s, -(kr_s * X_{s+1}))     d_s = flux_{s-1} - flux_s
+ *   stage  : T = fma(h, d, X)                       sum: a = k1, a = fma(2, k2, a), a = fma(2, k3, a), a = a + k4
+ *   update : X = fma(dt/6, a, X)
+ * fma() is the C99 correctly rounded fused multiply-add (hardware vfmadd through glibc's ifunc, or exact software);
+ * everything else is compiled with -ffp-contract=off, so these are the only fused operations.  With identical rate
+ * constants the trajectories are bit-identical to the device's. */
 static void chain_rhs(const double *X, const double *kf, const double *kr, int S, double *d) {
-    for (int s = 0; s <= S; ++s) d[s] = 0.0;
+    double prev = 0.0;
     for (int s = 0; s < S; ++s) {
-        double flux = kf[s] * X[s] - kr[s] * X[s + 1];
-        d[s] -= flux;
-        d[s + 1] += flux;
+        double back = kr[s] * X[s + 1];
+        double flux = fma(kf[s], X[s], -back);
+        d[s] = prev - flux;
+        prev = flux;
     }
+    d[S] = prev;
 }
 
 static double f_rk4_chain(const double *x, int k, const double *par) {
     int S = k / 2, nsteps = (int)par[1];
     double dt = par[0];
-    double X[ORC_MAX_K / 2 + 1], T[ORC_MAX_K / 2 + 1], k1[ORC_MAX_K / 2 + 1], k2[ORC_MAX_K / 2 + 1],
-        k3[ORC_MAX_K / 2 + 1], k4[ORC_MAX_K / 2 + 1];
+    double h2 = 0.5 * dt, h6 = dt / 6.0;
+    double X[ORC_MAX_K / 2 + 1], T[ORC_MAX_K / 2 + 1], a[ORC_MAX_K / 2 + 1], d[ORC_MAX_K / 2 + 1];
     for (int s = 0; s <= S; ++s) X[s] = 0.0;
     X[0] = 1.0;
     for (int it = 0; it < nsteps; ++it) {
-        chain_rhs(X, x, x + S, S, k1);
-        for (int s = 0; s <= S; ++s) T[s] = X[s] + (0.5 * dt) * k1[s];
-        chain_rhs(T, x, x + S, S, k2);
-        for (int s = 0; s <= S; ++s) T[s] = X[s] + (0.5 * dt) * k2[s];
-        chain_rhs(T, x, x + S, S, k3);
-        for (int s = 0; s <= S; ++s) T[s] = X[s] + dt * k3[s];
-        chain_rhs(T, x, x + S, S, k4);
-        for (int s = 0; s <= S; ++s) X[s] = X[s] + (dt / 6.0) * (k1[s] + 2.0 * k2[s] + 2.0 * k3[s] + k4[s]);
+        chain_rhs(X, x, x + S, S, d);
+        for (int s = 0; s <= S; ++s) { a[s] = d[s]; T[s] = fma(h2, d[s], X[s]); }
+        chain_rhs(T, x, x + S, S, d);
+        for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(h2, d[s], X[s]); }
+        chain_rhs(T, x, x + S, S, d);
+        for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(dt, d[s], X[s]); }
+        chain_rhs(T, x, x + S, S, d);
+        for (int s = 0; s <= S; ++s) { double t = a[s] + d[s]; X[s] = fma(h6, t, X[s]); }
     }
     return X[S];
 }

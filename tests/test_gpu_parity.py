@@ -8,7 +8,7 @@ import numpy
 import pytest
 
 from conftest import close
-from oracle import cport, halton as ohalton, objectives as ob, pipeline, saltelli as osalt, scale as oscale, sobol as osobol
+from oracle import cport, exact as oexact, halton as ohalton, objectives as ob, pipeline, saltelli as osalt, scale as oscale, sobol as osobol
 
 pytestmark = pytest.mark.gpu
 
@@ -193,13 +193,20 @@ def test_sample_flat_large_property(ctx):
                                    (10, 333, 3), (100, 70, 1), (20, 4098, 1), (23, 66, 1), (24, 1000, 1), (31, 130, 1),
                                    (50, 1026, 1), (7, 333, 1), (100, 130, 1), (150, 64, 1)])
 def test_indices_from_values(ctx, k, n, l):
+    """Contract tolerance (1e-10 relative or 1e-12 absolute) against the estimators evaluated in extended precision
+    (oracle/exact.py).  The data is deliberately ill-conditioned (values 10-13, variance 0.75: U_j - E_2 cancels seven
+    digits), where the fp64 numpy restatement itself sits 1e-13 - 3e-13 away from the exact answer; against that
+    restatement the distance may therefore reach the sum of both rounding noises (bounded at 2e-12 below)."""
     rng = numpy.random.RandomState(k * 1000 + n + l)
     vals = rng.rand(2 * n * (1 + k), l) * 3.0 + 10.0
+    res = ctx.indices_from_values(k, l, n, n, vals)
+    ex = oexact.indices(vals, k, n)
+    for name in NAMES:
+        close(getattr(res, name), ex[name].reshape(getattr(res, name).shape), rel=1e-10, abs_=1e-12)
     o = osalt.Objective(k, n, objective_vals=vals, verbose=False)
     v = osalt.Varsens(o, verbose=False)
-    res = ctx.indices_from_values(k, l, n, n, vals)
     for name in NAMES:
-        close(getattr(res, name), numpy.asarray(getattr(v, name)).reshape(getattr(res, name).shape), rel=1e-10, abs_=1e-9)
+        close(getattr(res, name), numpy.asarray(getattr(v, name)).reshape(getattr(res, name).shape), rel=1e-10, abs_=2e-12)
 
 
 def test_indices_from_values_reference_goldens(ctx, refgold):
@@ -220,11 +227,15 @@ def test_partials_tensor_path_matches_register_path(ctx, k, rows, monkeypatch):
     vals = rng.rand(2 + 2 * k, rows) * 2.0 + 5.0
     for flags in (vb_flags_second(), 0):
         monkeypatch.delenv("VS_GRAM_MMA", raising=False)
+        ctx.reload_env()                                                    # switches are read at ctx creation / on request only
         a = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
         a2 = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
         assert (a == a2).all()
         monkeypatch.setenv("VS_GRAM_MMA", "0")
+        ctx.reload_env()
         b = ctx.partials_from_values(k, 1, rows, vals, shift=[vals[0, 0]], flags=flags)
+        monkeypatch.delenv("VS_GRAM_MMA", raising=False)
+        ctx.reload_env()
         m = 2 + 2 * k
         # compare what the estimators read: sums + Gram rows 0,1 (first order) or the whole upper triangle
         want = vals @ vals.T
@@ -318,24 +329,31 @@ def test_fused_shards_equal_whole(ctx):
 
 
 def test_fused_host_permutation_is_pipelined_and_agrees(ctx, monkeypatch):
-    """vs_run_fused / vs_fused_partials with a HOST permutation of >= 2^21 rows cut the H2D copy into chunks and launch the
-    fused kernel per chunk (abi.cu: fused_partials_pipelined).  Same indices as the all-device call (chunk sums are added
-    in chunk order, so the last bits may differ), reproducible, and identical to the unpipelined host path per chunk."""
+    """vs_run_fused / vs_fused_partials with a HOST permutation of >= 2^19 rows cut the H2D copy into slices whose arrival
+    the ONE fused launch polls (abi.cu: fused_step).  The row -> warp assignment does not depend on how the permutation
+    arrives, so the result is bit-identical to the all-device call and to the unpipelined host path."""
     import torch
     k, n = 6, 1 << 22
     perm = perm_of(n)
+    l0 = ctx.launch_count()
     dev = ctx.run_fused(k, n, torch.from_numpy(perm.astype(numpy.int32)).cuda(), cport.OBJ_GFUNCTION, A6)
+    assert ctx.launch_count() - l0 == 1                                     # the whole step is one kernel launch
+    l0 = ctx.launch_count()
     host = ctx.run_fused(k, n, perm, cport.OBJ_GFUNCTION, A6)
-    host2 = ctx.run_fused(k, n, perm, cport.OBJ_GFUNCTION, A6)
+    assert ctx.launch_count() - l0 == 1
+    host2 = ctx.run_fused(k, n, torch.from_numpy(perm.astype(numpy.int32)).pin_memory(), cport.OBJ_GFUNCTION, A6)
     for name in NAMES:
-        close(getattr(host, name), getattr(dev, name), rel=1e-11, abs_=1e-12)
+        assert (getattr(host, name) == getattr(dev, name)).all()
         assert (getattr(host, name) == getattr(host2, name)).all()
-    # a shard with a host permutation: [n/4, n) = 3 * 2^20 rows -> 3 chunks
-    lo = n // 4
+    # a shard with a host permutation
+    lo = n // 4 + 3
     a = ctx.fused_partials(k, n, perm, cport.OBJ_GFUNCTION, A6, i_begin=lo, i_end=n)
     monkeypatch.setenv("VS_NO_PIPELINE", "1")
+    ctx.reload_env()
     b = ctx.fused_partials(k, n, perm, cport.OBJ_GFUNCTION, A6, i_begin=lo, i_end=n)
-    numpy.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)
+    monkeypatch.delenv("VS_NO_PIPELINE", raising=False)
+    ctx.reload_env()
+    assert (a == b).all()
 
 
 def test_fused_ishigami(ctx):
@@ -354,18 +372,38 @@ def test_eval_values_and_rk4(ctx):
     sc = _cabi.Scale(_cabi.SCALE_POWER, ref / 10.0, ref * 10.0)
     got = ctx.eval_values(k, n, perm_of(n), cport.OBJ_RK4_CHAIN, [0.01, 300], scale=sc)
     want = cport.values(k, n, cport.OBJ_RK4_CHAIN, [0.01, 300], scale=("power", ref / 10.0, ref * 10.0))
-    numpy.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-14)          # tolerance: FMA contraction over 300 steps
+    # rate constants within 2 ulp (pow) -> trajectories agree to rounding level; the RK4 arithmetic itself is pinned
+    numpy.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
     res = ctx.run_fused(k, n, perm_of(n), cport.OBJ_RK4_CHAIN, [0.01, 300], scale=sc)
-    assert_indices(res, cport.run(k, n, cport.OBJ_RK4_CHAIN, [0.01, 300], scale=("power", ref / 10.0, ref * 10.0)),
-                   names=("E_2", "var_y"))
-    for kk in (2, 6, 22, 40):                                                # templated and run-time link counts
+    assert_indices(res, cport.run(k, n, cport.OBJ_RK4_CHAIN, [0.01, 300], scale=("power", ref / 10.0, ref * 10.0)))
+    for kk in (2, 6, 20, 22, 40):                                            # templated and run-time link counts
+        # linear scaling is bit-exact, so device and oracle integrate identical rate constants: with the frozen RK4
+        # arithmetic (device.cuh RK4Chain / oracle.c f_rk4_chain) the trajectories must be BIT-IDENTICAL
         r = numpy.linspace(0.5, 2.0, kk)
-        got = ctx.eval_values(kk, 16, perm_of(16), cport.OBJ_RK4_CHAIN, [0.02, 50], scale=_cabi.Scale(_cabi.SCALE_LINEAR, r * 0.5, r * 2))
-        want = cport.values(kk, 16, cport.OBJ_RK4_CHAIN, [0.02, 50], scale=("linear", r * 0.5, r * 2))
-        numpy.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-15)
+        got = ctx.eval_values(kk, 16, perm_of(16), cport.OBJ_RK4_CHAIN, [0.02, 250], scale=_cabi.Scale(_cabi.SCALE_LINEAR, r * 0.5, r * 2))
+        want = cport.values(kk, 16, cport.OBJ_RK4_CHAIN, [0.02, 250], scale=("linear", r * 0.5, r * 2))
+        assert (got == want).all(), "k=%d: %d of %d trajectories differ" % (kk, int((got != want).sum()), got.size)
     got = ctx.eval_values(6, 100, perm_of(100), cport.OBJ_GFUNCTION, A6, i_begin=10, i_end=77)
     want = cport.values(6, 100, cport.OBJ_GFUNCTION, A6, i0=10, i1=77)
     numpy.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+def test_c5_rk4_frozen_spec_all_indices(ctx):
+    """BASELINE config 5 at its frozen spec (k=20 rate constants, scale.magnitude(ref, orders=1), dt=0.01, 1000 steps,
+    objective X_10(T)) at n = 2^14: ALL eight outputs against the long-double C oracle, contract tolerance."""
+    from varsens_b200 import _cabi
+    k, n = 20, 1 << 14
+    ref = numpy.array([1.0] * 10 + [0.5] * 10)
+    lo, up = ref / 10.0, ref * 10.0                                          # scale.py:121-122 with orders=1, base=10
+    sc = _cabi.Scale(_cabi.SCALE_POWER, lo, up)
+    p = perm_of(n)
+    res = ctx.run_fused(k, n, p, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=sc)
+    want = cport.run(k, n, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=("power", lo, up))
+    assert_indices(res, want)
+    # a window of the 1000-step trajectories themselves (rate constants within 2 ulp -> rounding-level agreement)
+    got = ctx.eval_values(k, n, p, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=sc, i_begin=5000, i_end=5064)
+    ref_v = cport.values(k, n, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=("power", lo, up), i0=5000, i1=5064)
+    numpy.testing.assert_allclose(got, ref_v, rtol=1e-12, atol=1e-300)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -507,13 +545,19 @@ def test_fused_k20_n2p18_against_c_oracle(ctx):
     assert_indices(res, cport.run(20, n, cport.OBJ_GFUNCTION, A20))
 
 
-def test_fused_full_size_c3_properties(ctx):
-    """BASELINE config 3 (k=20, n=2^24): closed-form truths (test_g_function.py:20-50) to 3e-3, the generic and
-    separable kernels agree to 1e-10, and a 2-shard split reproduces the single launch."""
+def test_fused_full_size_c3(ctx):
+    """BASELINE config 3 at FULL size (k=20, n=2^24, 704,643,072 evaluations): all eight outputs against the long-double
+    C/OpenMP oracle within the contract tolerance (1e-10 relative or 1e-12 absolute); closed-form truths
+    (test_g_function.py:20-50) to 3e-3; the generic and separable kernels agree; a 2-shard split reproduces the single launch;
+    the host-permutation (e2e) call is bit-identical to the resident one."""
     from varsens_b200 import _cabi
+    import torch
     k, n = 20, 1 << 24
     p = perm_of(n)
-    res = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20)
+    pd = torch.from_numpy(p.astype(numpy.int32)).cuda()
+    res = ctx.run_fused(k, n, pd, cport.OBJ_GFUNCTION, A20)
+    want = cport.run(k, n, cport.OBJ_GFUNCTION, A20, perm=p)
+    assert_indices(res, want)
     var = float(res.var_y[0])
     assert abs(var - ob.g_var(A20)) < 3e-3 and abs(float(res.E_2[0]) - 1.0) < 3e-3
     truth = ob.g_truth(A20)
@@ -524,13 +568,30 @@ def test_fused_full_size_c3_properties(ctx):
         assert abs(res.sens_2[i, 0, j, 0] * var - ob.g_truth_2(A20, i, j)) < 3e-3
         assert abs(res.sens_2n[i, 0, j, 0] * var - ob.g_truth_vnc(A20, [i, j])) < 3e-3
     assert numpy.allclose(res.sens_2[:, 0, :, 0], res.sens_2[:, 0, :, 0].T, rtol=0, atol=1e-15)
-    sep = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20, flags=_cabi.FLAG_SECOND_ORDER | _cabi.FLAG_SEPARABLE)
+    host = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, A20)
     for name in NAMES:
-        close(getattr(sep, name), getattr(res, name))
-    import torch
-    pd = torch.from_numpy(p.astype(numpy.int32)).cuda()
+        assert (getattr(host, name) == getattr(res, name)).all()
+    sep = ctx.run_fused(k, n, pd, cport.OBJ_GFUNCTION, A20, flags=_cabi.FLAG_SECOND_ORDER | _cabi.FLAG_SEPARABLE)
+    assert_indices(sep, want)
     acc = ctx.fused_partials(k, n, pd, cport.OBJ_GFUNCTION, A20, i_begin=0, i_end=n // 2 + 7)
     acc = acc + ctx.fused_partials(k, n, pd, cport.OBJ_GFUNCTION, A20, i_begin=n // 2 + 7, i_end=n)
     two = ctx.finalize(k, 1, n, acc)
-    for name in NAMES:
-        close(getattr(two, name), getattr(res, name))
+    assert_indices(two, want)
+
+
+def test_fused_full_size_c2_ishigami(ctx):
+    """BASELINE config 2 at FULL size (Ishigami, k=3, n=2^22, scale.linear(-pi, pi)): all eight outputs against the
+    long-double C oracle within the contract tolerance, and the analytic indices to 2e-3."""
+    from varsens_b200 import _cabi
+    pi = math.pi
+    n = 1 << 22
+    p = perm_of(n)
+    sc = _cabi.Scale(_cabi.SCALE_LINEAR, numpy.full(3, -pi), numpy.full(3, pi))
+    res = ctx.run_fused(3, n, p, cport.OBJ_ISHIGAMI, [7.0, 0.1], scale=sc)
+    assert_indices(res, cport.run(3, n, cport.OBJ_ISHIGAMI, [7.0, 0.1], scale=("linear", [-pi] * 3, [pi] * 3), perm=p))
+    assert abs(float(res.var_y[0]) - 13.8446) < 2e-2
+    for got, truth in zip(res.sens[:, 0], (0.3139, 0.4424, 0.0)):
+        assert abs(got - truth) < 2e-3
+    for got, truth in zip(res.sens_t[:, 0], (0.5576, 0.4424, 0.2437)):
+        assert abs(got - truth) < 2e-3
+    assert abs(res.sens_2[0, 0, 2, 0] - 0.5576) < 2e-3 and abs(res.sens_2[0, 0, 1, 0] - 0.7563) < 2e-3

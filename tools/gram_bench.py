@@ -36,6 +36,7 @@ def main():
                 os.environ["VS_GRAM_MMA"] = "0"
             else:
                 os.environ.pop("VS_GRAM_MMA", None)
+            ctx.reload_env()
             best = []
             for it in range(6):
                 flush.zero_()

@@ -11,6 +11,7 @@ for k in (4, 6, 8, 10, 11, 12, 14, 15, 16, 18, 20):
     out = []
     for v in ("5", "6"):
         os.environ["VS_FUSED_VARIANT"] = v
+        ctx.reload_env()
         ts = []
         for _ in range(4):
             r = ctx.run_fused(k, n, perm, _cabi.OBJ_GFUNCTION, a)

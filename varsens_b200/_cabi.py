@@ -24,11 +24,14 @@ SYMBOLS = (
     "vs_ctx_synchronize", "vs_ctx_launch_count", "vs_halton_bases", "vs_halton_terms", "vs_partials_len",
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
     "vs_finalize_device", "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
+    "vs_ctx_reload_env", "vs_ctx_set_halton_mode", "vs_halton_terms_mode", "vs_run_fused_p2p", "vs_last_tail_ns",
 )
+HALTON_DIVIDE, HALTON_RECIPROCAL, HALTON_RUNNING_RECIPROCAL, HALTON_HORNER = 0, 1, 2, 3
+ERR_TIMEOUT = 6
 
 
 class VarsensError(RuntimeError):
-    pass
+    status = None
 
 
 class vs_scale(ctypes.Structure):
@@ -81,6 +84,12 @@ def lib():
         L.vs_fused_partials.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32,
                                         vp, i32]
         L.vs_run_fused.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, i32, P(vs_result)]
+        L.vs_run_fused_p2p.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), i32, vp, i32, u64, u64, i32, i32, i32, vp, vp,
+                                       ctypes.c_uint32, P(vs_result)]
+        L.vs_ctx_reload_env.argtypes = [vp]
+        L.vs_ctx_set_halton_mode.argtypes = [vp, i32]
+        L.vs_halton_terms_mode.argtypes = [i32, u64, i32, vp, vp, vp, u64, P(u64)]
+        L.vs_last_tail_ns.argtypes = [vp, i32, vp]
         L.vs_measure_fp64_peak.argtypes = [vp, P(ctypes.c_double)]
         L.vs_last_kernel_ms.argtypes = [vp, P(ctypes.c_float)]
         for name in SYMBOLS:
@@ -93,15 +102,19 @@ def lib():
 
 def check(status):
     if status != VS_OK:
-        raise VarsensError("libvarsens_b200: status %d: %s" % (status, lib().vs_last_error().decode()))
+        err = VarsensError("libvarsens_b200: status %d: %s" % (status, lib().vs_last_error().decode()))
+        err.status = status
+        raise err
 
 
 def _is_torch_tensor(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
-def buf(x, dtype=None):
-    """(pointer, mem flag, keepalive) for a numpy array or torch tensor (None -> NULL)."""
+def buf(x, dtype=None, out=False):
+    """(pointer, mem flag, keepalive) for a numpy array or torch tensor (None -> NULL).  ``out=True``: the library writes
+    into the buffer, so a numpy array must already be C-contiguous and of the right dtype (a silent copy would be
+    written instead of the caller's array)."""
     if x is None:
         return None, MEM_HOST, None
     if _is_torch_tensor(x):
@@ -113,6 +126,12 @@ def buf(x, dtype=None):
             if x.dtype not in (want, getattr(torch, "uint32", want)):
                 raise VarsensError("tensor dtype %s, expected %s" % (x.dtype, want))
         return ctypes.c_void_p(x.data_ptr()), (MEM_DEVICE if x.is_cuda else MEM_HOST), x
+    if out:
+        if not isinstance(x, numpy.ndarray) or not x.flags.c_contiguous or not x.flags.writeable or \
+                (dtype is not None and x.dtype != numpy.dtype(dtype)):
+            raise VarsensError("output buffer must be a writeable C-contiguous numpy array of dtype %s (or a torch tensor)"
+                               % (numpy.dtype(dtype).name if dtype is not None else "matching"))
+        return x.ctypes.data_as(ctypes.c_void_p), MEM_HOST, x
     a = numpy.ascontiguousarray(x, dtype=dtype)
     return a.ctypes.data_as(ctypes.c_void_p), MEM_HOST, a
 
@@ -220,6 +239,21 @@ class Context(object):
         else:
             ptr = int(cuda_stream_ptr) or 1
         check(lib().vs_ctx_set_stream(self._h, ctypes.c_void_p(ptr)))
+        self._stream_ptr = cuda_stream_ptr
+
+    def reload_env(self):
+        """Re-read the VS_* switches from the environment (they are otherwise read once, when the ctx is created)."""
+        check(lib().vs_ctx_reload_env(self._h))
+
+    def set_halton_mode(self, mode):
+        """Arithmetic of the Halton radical inverse (HALTON_DIVIDE / _RECIPROCAL / _RUNNING_RECIPROCAL / _HORNER)."""
+        check(lib().vs_ctx_set_halton_mode(self._h, int(mode)))
+
+    def last_tail_ns(self, k):
+        """ns spent in {combine+pack, peer stores, wait for peers, sum+estimators} by the tail of the last fused step."""
+        a = numpy.zeros(4)
+        check(lib().vs_last_tail_ns(self._h, int(k), a.ctypes.data_as(ctypes.c_void_p)))
+        return a
 
     def launch_count(self):
         return int(lib().vs_ctx_launch_count(self._h))
@@ -238,7 +272,7 @@ class Context(object):
     def halton(self, k, first_index, count, scale=IDENTITY, out=None):
         out = numpy.empty((int(count), int(k))) if out is None else out
         sp, keep = scale.c_struct(k)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_halton(self._h, int(k), int(first_index), int(count), sp, op, om))
         return out
 
@@ -248,7 +282,7 @@ class Context(object):
         if d.shape != (k, 32):
             raise VarsensError("dirnums must have shape (k, 32)")
         sp, keep = scale.c_struct(k)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_sobol(self._h, int(k), int(first_point), int(count), d.ctypes.data_as(ctypes.c_void_p),
                              int(bool(quantize6)), sp, op, om))
         return out
@@ -260,7 +294,7 @@ class Context(object):
         sp, keep = scale.c_struct(k)
         pp, pm, pk = buf(perm, numpy.uint32)
         rp, rm, rk = buf(raw, numpy.float64)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_sample_flat(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(row_begin),
                                    int(row_end), op, om))
         return out
@@ -274,7 +308,7 @@ class Context(object):
         sp, keep = scale.c_struct(k)
         pp, pm, pk = buf(perm, numpy.uint32)
         rp, rm, rk = buf(raw, numpy.float64)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_eval_values(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
                                    par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end), op, om))
         return out
@@ -285,7 +319,7 @@ class Context(object):
         fp, fm, fk = buf(fvals, numpy.float64)
         sh = None if shift is None else numpy.ascontiguousarray(shift, dtype=numpy.float64)
         shp = None if sh is None else sh.ctypes.data_as(ctypes.c_void_p)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_partials_from_values(self._h, int(k), int(l), int(rows), fp, fm, shp, int(flags), op, om))
         return out
 
@@ -300,7 +334,7 @@ class Context(object):
     def finalize_device(self, k, l, n, partials, out, flags=FLAG_SECOND_ORDER, rows=None):
         """vs_finalize_device: results stay in the CUDA tensor `out` (Result.from_flat unpacks a host copy); nothing syncs."""
         pp, pm, pk = buf(partials, numpy.float64)
-        op, om, ok_ = buf(out, numpy.float64)
+        op, om, ok_ = buf(out, numpy.float64, out=True)
         if pm != MEM_DEVICE or om != MEM_DEVICE:
             raise VarsensError("finalize_device needs device tensors")
         check(lib().vs_finalize_device(self._h, int(k), int(l), int(n), int(n if rows is None else rows), pp, int(flags), op))
@@ -338,7 +372,7 @@ class Context(object):
         sp, keep = scale.c_struct(k)
         pp, pm, pk = buf(perm, numpy.uint32)
         rp, rm, rk = buf(raw, numpy.float64)
-        op, om, _ = buf(out, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_fused_partials(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
                                       par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end),
                                       int(flags), op, om))
@@ -356,18 +390,39 @@ class Context(object):
         return res
 
 
-def halton_terms(k, max_index):
-    """Host-only: the library's term table (bases, ndigits, offsets, terms)."""
+def _run_fused_p2p(self, k, n, perm, objective, params, world_size, rank, peer_bufs, peer_flags, epoch, i_begin, i_end,
+                   discard=0, scale=IDENTITY, raw=None, flags=FLAG_SECOND_ORDER):
+    """vs_run_fused_p2p: this rank's shard [i_begin,i_end) of the fused step, all-reduce over NVLink peer memory and
+    estimators inside the ONE kernel launch; returns the Result (identical bits on every rank)."""
+    res = Result(k, 1, bool(flags & FLAG_SECOND_ORDER))
+    cs = res.c_struct()
+    par = numpy.ascontiguousarray(params, dtype=numpy.float64)
+    sp, keep = scale.c_struct(k)
+    pp, pm, pk = buf(perm, numpy.uint32)
+    rp, rm, rk = buf(raw, numpy.float64)
+    pb = (ctypes.c_uint64 * world_size)(*[int(x) for x in peer_bufs])
+    pf = (ctypes.c_uint64 * world_size)(*[int(x) for x in peer_flags])
+    check(lib().vs_run_fused_p2p(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                                 par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end), int(flags),
+                                 int(world_size), int(rank), pb, pf, int(epoch), ctypes.byref(cs)))
+    return res
+
+
+Context.run_fused_p2p = _run_fused_p2p
+
+
+def halton_terms(k, max_index, mode=HALTON_DIVIDE):
+    """Host-only: the library's term table (bases, ndigits, offsets, terms) in one of the term-table modes."""
     L = lib()
     bases = numpy.zeros(k, dtype=numpy.uint32)
     check(L.vs_halton_bases(int(k), bases.ctypes.data_as(ctypes.c_void_p)))
     cnt = ctypes.c_uint64()
     nd = numpy.zeros(k, dtype=numpy.uint32)
     off = numpy.zeros(k, dtype=numpy.uint32)
-    check(L.vs_halton_terms(int(k), int(max_index), nd.ctypes.data_as(ctypes.c_void_p),
-                            off.ctypes.data_as(ctypes.c_void_p), None, 0, ctypes.byref(cnt)))
+    check(L.vs_halton_terms_mode(int(k), int(max_index), int(mode), nd.ctypes.data_as(ctypes.c_void_p),
+                                 off.ctypes.data_as(ctypes.c_void_p), None, 0, ctypes.byref(cnt)))
     terms = numpy.zeros(int(cnt.value))
-    check(L.vs_halton_terms(int(k), int(max_index), nd.ctypes.data_as(ctypes.c_void_p),
-                            off.ctypes.data_as(ctypes.c_void_p), terms.ctypes.data_as(ctypes.c_void_p),
-                            int(cnt.value), ctypes.byref(cnt)))
+    check(L.vs_halton_terms_mode(int(k), int(max_index), int(mode), nd.ctypes.data_as(ctypes.c_void_p),
+                                 off.ctypes.data_as(ctypes.c_void_p), terms.ctypes.data_as(ctypes.c_void_p),
+                                 int(cnt.value), ctypes.byref(cnt)))
     return bases, nd, off, terms

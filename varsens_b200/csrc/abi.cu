@@ -43,13 +43,8 @@ int check_common(vs_ctx *c, int k) {
     return VS_OK;
 }
 
-int copy_result(vs_ctx *c, int k, int l, int flags, const double *res_dev, vs_result *r) {
-    size_t len = result_len(k, l);
-    std::vector<double> h(len);
-    VS_CUDA(cudaMemcpyAsync(h.data(), res_dev, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    VS_CUDA(cudaStreamSynchronize(c->stream));
+void unpack_result(const double *p, int k, int l, int flags, vs_result *r) {
     size_t kl = (size_t)k * l;
-    const double *p = h.data();
     auto take = [&](double *dst, size_t cnt) {
         if (dst) memcpy(dst, p, cnt * sizeof(double));
         p += cnt;
@@ -64,6 +59,24 @@ int copy_result(vs_ctx *c, int k, int l, int flags, const double *res_dev, vs_re
         take(r->sens_2, kl * kl);
         take(r->sens_2n, kl * kl);
     }
+}
+
+// Estimators from partial sums in HBM: finalize_kernel writes straight into the ctx's mapped host buffer (no copy call).
+int finalize_to_host(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials_dev, int flags, vs_result *r) {
+    VS_TRY(ensure_host_res(c, result_len(k, l) + HOST_RES_EXTRA));
+    VS_TRY(launch_finalize(c, k, l, n, rows, partials_dev, flags, c->host_res));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    unpack_result(c->host_res, k, l, flags, r);
+    return VS_OK;
+}
+
+// Results the tail of the fused kernel left in the mapped host buffer (after the stream has been synchronised).
+int take_tail_result(vs_ctx *c, int k, int flags, vs_result *r) {
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    const double *x = c->host_res + result_len(k, 1);
+    VS_REQUIRE(x[0] == 0.0, VS_ERR_TIMEOUT, "peer-memory all-reduce: a rank did not publish its partial sums within %d ms",
+               c->opt.p2p_timeout_ms);
+    unpack_result(c->host_res, k, 1, flags, r);
     return VS_OK;
 }
 
@@ -179,15 +192,13 @@ extern "C" int vs_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, c
     VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials && result, VS_ERR_ARG, "bad arguments");
     const void *pdev = nullptr;
     VS_TRY(stage_in(c, c->part_buf, partials, partials_mem, vs_partials_len(k, l) * sizeof(double), &pdev));
-    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, l, n, rows, (const double *)pdev, flags, (double *)c->res_buf.p));
-    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+    return finalize_to_host(c, k, l, n, rows, (const double *)pdev, flags, result);
 }
 
 extern "C" int vs_finalize_device(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *partials_dev, int flags,
                                   double *result_dev) {
-    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
-    VS_REQUIRE(k >= 1 && l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result_dev, VS_ERR_ARG, "bad arguments");
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result_dev, VS_ERR_ARG, "bad arguments");
     return launch_finalize(c, k, l, n, rows, partials_dev, flags, result_dev);
 }
 
@@ -198,7 +209,6 @@ extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, ui
     VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result, VS_ERR_ARG, "bad arguments");
     VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && peer_flags && epoch >= 1,
                VS_ERR_ARG, "bad peer description");
-    VS_REQUIRE(partials_dev != c->part_buf.p, VS_ERR_ARG, "partials_dev must be a caller buffer");
     // the two pointer tables travel as kernel-visible device arrays (dir_buf: world_size * 2 pointers)
     VS_TRY(ensure(c, c->peer_buf, 2 * 64 * sizeof(uint64_t)));
     uint64_t *tab = (uint64_t *)c->peer_buf.p;
@@ -208,10 +218,14 @@ extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, ui
         c->peer_tab = want;
         VS_CUDA(cudaMemcpyAsync(tab, c->peer_tab.data(), 128 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
     }
-    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
-    VS_TRY(launch_p2p_reduce_finalize(c, k, l, n, rows, world_size, rank, tab, tab + 64, epoch, partials_dev, flags,
-                                      (double *)c->res_buf.p));
-    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+    VS_TRY(ensure_host_res(c, result_len(k, l) + HOST_RES_EXTRA));
+    c->host_res[result_len(k, l)] = 0.0;
+    VS_TRY(launch_p2p_reduce_finalize(c, k, l, n, rows, world_size, rank, tab, tab + 64, epoch, partials_dev, flags, c->host_res));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    VS_REQUIRE(c->host_res[result_len(k, l)] == 0.0, VS_ERR_TIMEOUT,
+               "peer-memory all-reduce: a rank did not publish its partial sums within %d ms", c->opt.p2p_timeout_ms);
+    unpack_result(c->host_res, k, l, flags, result);
+    return VS_OK;
 }
 
 extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, const double *fvals, int fvals_mem,
@@ -226,87 +240,96 @@ extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint6
     VS_TRY(ensure(c, c->part_buf, vs_partials_len(k, l) * sizeof(double)));
     VS_TRY(launch_partials_from_values(c, k, l, rows, (const double *)fdev, (const double *)c->misc_buf.p, flags,
                                        (double *)c->part_buf.p));
-    VS_TRY(ensure(c, c->res_buf, result_len(k, l) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, l, n, rows, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
-    return copy_result(c, k, l, flags, (const double *)c->res_buf.p, result);
+    return finalize_to_host(c, k, l, n, rows, (const double *)c->part_buf.p, flags, result);
 }
 
-// Sum of `nchunk` partial-sum vectors in chunk order (fixed order -> reproducible).
-__global__ void __launch_bounds__(256) sum_chunks_kernel(int plen, int nchunk, const double *__restrict__ in, double *__restrict__ out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= plen) return;
-    double s = 0.0;
-    for (int ch = 0; ch < nchunk; ++ch) s += in[(size_t)ch * plen + e];
-    out[e] = s;
-}
+// ---------------------------------------------------------------------------------------------------------------------
+// The fused step.  One kernel launch does everything (fused_impl.cuh): generation + evaluation + Gram, fixed-order
+// combine by the last CTA, and -- depending on FusedReq::mode -- the packed partial sums, the estimators, or the
+// peer-memory all-reduce followed by the estimators, with the results written to mapped host memory.
+//
+// Host permutation (VS_MEM_HOST): the H2D copy (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over PCIe) is cut into
+// growing slices on the copy stream, each followed by an 8-byte copy that bumps an arrival counter in HBM; the SAME single
+// launch polls that counter before it touches a slice, so only the first small slice is exposed and no launch is repeated.
+// The copies are enqueued before the launch (a serialising tool -- compute-sanitizer, CUDA_LAUNCH_BLOCKING -- cannot deadlock).
+// ---------------------------------------------------------------------------------------------------------------------
+static const uint64_t PIPE_MIN_ROWS = 1ull << 19;
 
-// Host permutation + fused kernel: the H2D copy of the permutation (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over
-// PCIe) is cut into 2-4 growing slices on the copy stream and the fused kernel is launched per chunk as its slice arrives, so only the
-// first slice is exposed.  Chunk partial sums are added in chunk order.  (vs_run_fused / vs_fused_partials with VS_MEM_HOST.)
-static const uint64_t PIPE_MIN_ROWS = 1ull << 21;
-
-static int fused_partials_pipelined(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm_host, const vs_scale *scale,
-                                    int objective, const double *params, int n_params, uint64_t i_begin, uint64_t i_end, int flags,
-                                    double *partials_dev) {
+static int fused_step(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem, const double *raw,
+                      int raw_mem, const vs_scale *scale, int objective, const double *params, int n_params, uint64_t i_begin,
+                      uint64_t i_end, int flags, double *partials_dev, FusedReq *req, bool *finalized) {
+    *finalized = false;
     const uint64_t rows = i_end - i_begin;
-    // Slices grow: the first one is small so that little of the copy is exposed, the later ones are large so that few
-    // kernel start-ups and tails are paid (at k = 20 a slice computes ~4x longer than it copies).  Sixteenths of the rows.
-    static const int cuts[5][5] = {{0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};
-    int nchunk = (int)(rows >> 20);
-    if (nchunk > 4) nchunk = 4;
-    const size_t plen = vs_partials_len(k, 1);
-    VS_TRY(ensure(c, c->perm_buf, rows * sizeof(uint32_t)));
-    VS_TRY(ensure(c, c->pipe_buf, (size_t)nchunk * plen * sizeof(double)));
-    while ((int)c->pipe_ev.size() < nchunk + 1) {
-        cudaEvent_t e;
-        VS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->pipe_ev.push_back(e);
-    }
-    SourceDev src;
-    const uint32_t *perm_dev = (const uint32_t *)c->perm_buf.p - i_begin;          // indexed by the absolute base row
-    VS_TRY(make_source(c, k, n, discard, perm_dev, VS_MEM_DEVICE, i_begin, rows, nullptr, VS_MEM_HOST, &src));
+    const bool fused = fused_supported(k, objective, flags) && !(c->opt.halton_mode == VS_HALTON_HORNER && !raw);
+    const bool tail_ok = fused && fused_tail_supported(c, k, objective, flags);
     ScaleDev s;
-    VS_TRY(get_scale(c, k, scale, &s));
     ObjectiveDev od;
-    VS_TRY(get_objective(c, k, objective, params, n_params, &od));
-    // the copies may not overwrite the staging buffer before earlier work on the compute stream has finished reading it
-    VS_CUDA(cudaEventRecord(c->pipe_ev[nchunk], c->stream));
-    VS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[nchunk], 0));
-    auto bound = [&](int ch) { return i_begin + rows / 16 * (uint64_t)cuts[nchunk][ch] + (ch == nchunk ? rows % 16 : 0); };
-    for (int ch = 0; ch < nchunk; ++ch) {
-        const uint64_t b = bound(ch), e = bound(ch + 1);
-        VS_CUDA(cudaMemcpyAsync((uint32_t *)c->perm_buf.p + (b - i_begin), perm_host + b, (e - b) * sizeof(uint32_t),
-                                cudaMemcpyHostToDevice, c->copy_stream));
-        VS_CUDA(cudaEventRecord(c->pipe_ev[ch], c->copy_stream));
-    }
-    for (int ch = 0; ch < nchunk; ++ch) {
-        VS_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_ev[ch], 0));
-        VS_TRY(launch_fused(c, k, src, s, od, bound(ch), bound(ch + 1), flags, (double *)c->pipe_buf.p + (size_t)ch * plen));
-    }
-    sum_chunks_kernel<<<(unsigned)((plen + 255) / 256), 256, 0, c->stream>>>((int)plen, nchunk, (const double *)c->pipe_buf.p, partials_dev);
-    c->launches++;
-    VS_CUDA(cudaGetLastError());
-    return VS_OK;
-}
-
-static int fused_partials_dev(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
-                              const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
-                              int n_params, uint64_t i_begin, uint64_t i_end, int flags, double *partials_dev) {
-    if (perm_mem == VS_MEM_HOST && !raw && i_end - i_begin >= PIPE_MIN_ROWS && fused_supported(k, objective, flags) && !capturing(c) &&
-        !getenv("VS_NO_PIPELINE"))
-        return fused_partials_pipelined(c, k, n, discard, perm, scale, objective, params, n_params, i_begin, i_end, flags, partials_dev);
     SourceDev src;
-    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, i_end - i_begin, raw, raw_mem, &src));
-    ScaleDev s;
+    if (perm_mem == VS_MEM_HOST && !raw && tail_ok && rows >= PIPE_MIN_ROWS && !capturing(c) && !c->opt.no_pipeline) {
+        VS_REQUIRE(perm, VS_ERR_ARG, "perm is NULL");
+        // slice boundaries in 32-row batches (a batch is one 128-byte line of the staged permutation)
+        static const int cuts64[] = {1, 4, 12, 24, 40, 64};                    // 64ths of the batches: growing slices
+        const uint64_t nbatch = (rows + 31) / 32;
+        int nchunk = 0;
+        uint64_t prev = 0;
+        for (int ci = 0; ci < 6; ++ci) {
+            uint64_t e = ci == 5 ? nbatch : nbatch * (uint64_t)cuts64[ci] / 64;
+            if (e <= prev) continue;
+            req->chunk_end_batch[nchunk++] = (uint32_t)e;
+            prev = e;
+        }
+        req->nchunk = nchunk;
+        VS_TRY(ensure(c, c->perm_buf, rows * sizeof(uint32_t)));
+        if (!c->ticket_buf.p) {
+            VS_TRY(ensure(c, c->ticket_buf, 256));
+            VS_CUDA(cudaMemsetAsync(c->ticket_buf.p, 0, 256, c->stream));
+        }
+        if (c->pipe_ev.empty()) {
+            cudaEvent_t e;
+            VS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->pipe_ev.push_back(e);
+        }
+        const uint32_t *perm_dev = (const uint32_t *)c->perm_buf.p - i_begin;      // indexed by the absolute base row
+        VS_TRY(make_source(c, k, n, discard, perm_dev, VS_MEM_DEVICE, i_begin, rows, nullptr, VS_MEM_HOST, &src));
+        VS_TRY(get_scale(c, k, scale, &s));
+        VS_TRY(get_objective(c, k, objective, params, n_params, &od));
+        // the copies may not overwrite the staging buffer (or the counter) before earlier work on the compute stream is done
+        VS_CUDA(cudaEventRecord(c->pipe_ev[0], c->stream));
+        VS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[0], 0));
+        unsigned long long *arrive = (unsigned long long *)((char *)c->ticket_buf.p + 64);
+        req->arrive_dev = arrive;
+        req->arrive_base = c->seq;
+        uint64_t b0 = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            uint64_t b1 = (uint64_t)req->chunk_end_batch[ch] * 32;
+            if (b1 > rows) b1 = rows;
+            VS_CUDA(cudaMemcpyAsync((uint32_t *)c->perm_buf.p + b0, perm + i_begin + b0, (b1 - b0) * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, c->copy_stream));
+            unsigned long long *slot = c->host_seq + (c->seq % 64);
+            *slot = ++c->seq;
+            VS_CUDA(cudaMemcpyAsync(arrive, slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->copy_stream));
+            b0 = b1;
+        }
+        return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev, req, finalized);
+    }
+    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, rows, raw, raw_mem, &src));
     VS_TRY(get_scale(c, k, scale, &s));
-    ObjectiveDev od;
     VS_TRY(get_objective(c, k, objective, params, n_params, &od));
-    if (fused_supported(k, objective, flags))
-        return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev);
+    if (fused) {
+        if (!tail_ok || capturing(c)) {                  // legacy variants (and graph capture) produce partial sums only
+            FusedReq plain;
+            if (!partials_dev) {
+                VS_TRY(ensure(c, c->part_buf, vs_partials_len(k, 1) * sizeof(double)));
+                partials_dev = (double *)c->part_buf.p;
+            }
+            return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev, tail_ok ? &plain : nullptr, finalized);
+        }
+        return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev, req, finalized);
+    }
     // Two-phase path on the GPU: values to HBM scratch, then the Gram reduction.
     VS_REQUIRE(!(flags & VS_FLAG_SEPARABLE), VS_ERR_UNSUPPORTED, "VS_FLAG_SEPARABLE needs a fused kernel (objective %d, k=%d)",
                objective, k);
-    uint64_t rows = i_end - i_begin;
+    VS_REQUIRE(partials_dev, VS_ERR_ARG, "two-phase path needs a partial-sum buffer");
     VS_TRY(ensure(c, c->io_buf, rows * (uint64_t)(2 + 2 * k) * sizeof(double)));
     VS_TRY(launch_eval_values(c, k, src, s, od, i_begin, i_end, (double *)c->io_buf.p));
     // common shift f(M_1[0]) must not depend on the shard: evaluate base row 0 separately
@@ -340,8 +363,10 @@ extern "C" int vs_fused_partials(vs_ctx *c, int k, uint64_t n, uint64_t discard,
         VS_CUDA(cudaMemsetAsync(o.dev, 0, plen * sizeof(double), c->stream));
         return o.end();
     }
-    VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, i_begin,
-                              i_end, flags, (double *)o.dev));
+    FusedReq req;
+    bool finalized = false;
+    VS_TRY(fused_step(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, i_begin, i_end, flags,
+                      (double *)o.dev, &req, &finalized));
     VS_TRY(o.end());
     // all-device call: only enqueued (the caller's next op on the same stream, e.g. the all-reduce, orders after it);
     // with a host input the staged copy must have left the caller's buffer before we return
@@ -356,11 +381,63 @@ extern "C" int vs_run_fused(vs_ctx *c, int k, uint64_t n, uint64_t discard, cons
     VS_TRY(check_common(c, k));
     VS_REQUIRE(n >= 2 && result, VS_ERR_ARG, "bad arguments");
     VS_TRY(ensure(c, c->part_buf, vs_partials_len(k, 1) * sizeof(double)));
-    VS_TRY(fused_partials_dev(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, 0, n, flags,
-                              (double *)c->part_buf.p));
-    VS_TRY(ensure(c, c->res_buf, result_len(k, 1) * sizeof(double)));
-    VS_TRY(launch_finalize(c, k, 1, n, n, (const double *)c->part_buf.p, flags, (double *)c->res_buf.p));
-    return copy_result(c, k, 1, flags, (const double *)c->res_buf.p, result);
+    FusedReq req;
+    req.mode = 1;
+    req.n_total = req.rows_total = n;
+    bool finalized = false;
+    VS_TRY(fused_step(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, 0, n, flags,
+                      (double *)c->part_buf.p, &req, &finalized));
+    if (finalized) return take_tail_result(c, k, flags, result);
+    return finalize_to_host(c, k, 1, n, n, (const double *)c->part_buf.p, flags, result);
+}
+
+extern "C" int vs_run_fused_p2p(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                                const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
+                                int n_params, uint64_t i_begin, uint64_t i_end, int flags, int world_size, int rank,
+                                const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch, vs_result *result) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 2 && i_begin < i_end && i_end <= n && result, VS_ERR_ARG, "bad arguments (every rank needs at least one base row)");
+    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && peer_flags && epoch >= 1,
+               VS_ERR_ARG, "bad peer description");
+    VS_TRY(ensure(c, c->peer_buf, 2 * 64 * sizeof(uint64_t)));
+    uint64_t *tab = (uint64_t *)c->peer_buf.p;
+    std::vector<uint64_t> want(128, 0);
+    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags[r]; }
+    if (want != c->peer_tab) {                              // uploaded once per exchange, not per call
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        c->peer_tab = want;
+        VS_CUDA(cudaMemcpyAsync(tab, c->peer_tab.data(), 128 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    VS_TRY(ensure(c, c->part_buf, 2 * vs_partials_len(k, 1) * sizeof(double)));
+    double *mine = (double *)c->part_buf.p + vs_partials_len(k, 1);       // [0, plen) is the scratch of the stand-alone exchange kernel
+    FusedReq req;
+    req.mode = 2;
+    req.n_total = req.rows_total = n;
+    req.world = world_size;
+    req.rank = rank;
+    req.epoch = epoch;
+    req.peer_bufs_dev = tab;
+    req.peer_flags_dev = tab + 64;
+    bool finalized = false;
+    VS_TRY(fused_step(c, k, n, discard, perm, perm_mem, raw, raw_mem, scale, objective, params, n_params, i_begin, i_end, flags,
+                      mine, &req, &finalized));
+    if (finalized) return take_tail_result(c, k, flags, result);
+    // kernels without the in-kernel tail (two-phase path, legacy variants): exchange + estimators in the stand-alone kernel
+    VS_TRY(ensure_host_res(c, result_len(k, 1) + HOST_RES_EXTRA));
+    c->host_res[result_len(k, 1)] = 0.0;
+    VS_TRY(launch_p2p_reduce_finalize(c, k, 1, n, n, world_size, rank, tab, tab + 64, epoch, mine, flags, c->host_res));
+    VS_CUDA(cudaStreamSynchronize(c->stream));
+    VS_REQUIRE(c->host_res[result_len(k, 1)] == 0.0, VS_ERR_TIMEOUT,
+               "peer-memory all-reduce: a rank did not publish its partial sums within %d ms", c->opt.p2p_timeout_ms);
+    unpack_result(c->host_res, k, 1, flags, result);
+    return VS_OK;
+}
+
+extern "C" int vs_last_tail_ns(vs_ctx *c, int k, double *ns4) {
+    VS_REQUIRE(c && ns4 && c->host_res, VS_ERR_ARG, "no fused step has run on this ctx");
+    const double *x = c->host_res + result_len(k, 1);
+    for (int i = 0; i < 4; ++i) ns4[i] = x[1 + i];
+    return VS_OK;
 }
 
 extern "C" int vs_measure_fp64_peak(vs_ctx *c, double *tflops) {

@@ -25,7 +25,24 @@ __device__ __forceinline__ double radical_inverse(const double *__restrict__ T, 
     return x;
 }
 
+// VS_HALTON_HORNER: x = (x + digit_j) / b from the most significant digit down (one fp64 division per digit).
+__device__ __forceinline__ double radical_inverse_horner(uint32_t b, uint64_t magic, uint32_t m) {
+    if (b == 2u) return (double)__brev(m) * 2.3283064365386962890625e-10;
+    unsigned char dig[32];
+    int nd = 0;
+    while (m != 0u) {
+        uint32_t q = (uint32_t)__umul64hi((uint64_t)m, magic);
+        dig[nd++] = (unsigned char)(m - q * b);
+        m = q;
+    }
+    double x = 0.0;
+    const double bd = (double)b;
+    for (int j = nd - 1; j >= 0; --j) x = __ddiv_rn(__dadd_rn(x, (double)dig[j]), bd);
+    return x;
+}
+
 __device__ __forceinline__ double halton_coord(const HaltonDev &h, int d, uint32_t m) {
+    if (h.mode == VS_HALTON_HORNER) return radical_inverse_horner(h.base[d], h.magic[d], m);
     return radical_inverse(h.terms + h.off[d], h.base[d], h.magic[d], m);
 }
 
@@ -83,6 +100,15 @@ struct Ishigami {
 };
 
 // Reversible chain, S links, S+1 species.  Register-resident for compile-time S.
+// FROZEN ARITHMETIC (the oracle, oracle/oracle.c: f_rk4_chain, performs exactly these roundings, so trajectories are
+// bit-identical given bit-identical rate constants): every product-sum below is ONE fused multiply-add where written as
+// fma(), one rounded multiply / add / subtract where written as __dmul_rn / __dadd_rn / __dsub_rn; nothing is left to the
+// compiler's contraction choices.
+//   flux_s = fma(kf_s, X_s, -(kr_s * X_{s+1}))     d_s = flux_{s-1} - flux_s
+//   stage  : T = fma(h, d, X)                       sum: a = k1, a = fma(2, k2, a), a = fma(2, k3, a), a = a + k4
+//   update : X = fma(dt/6, a, X)
+// (This is what nvcc's default contraction produced before it was pinned: the change cost nothing -- C5 runs at the same
+// 71 % of the FP64 peak.)
 template <int S>
 struct RK4Chain {
     double dt;
@@ -92,8 +118,8 @@ struct RK4Chain {
         double prev = 0.0;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            double flux = kf[s] * X[s] - kr[s] * X[s + 1];
-            d[s] = prev - flux;
+            double flux = fma(kf[s], X[s], -__dmul_rn(kr[s], X[s + 1]));
+            d[s] = __dsub_rn(prev, flux);
             prev = flux;
         }
         d[S] = prev;
@@ -106,26 +132,26 @@ struct RK4Chain {
 #pragma unroll
         for (int s = 0; s <= S; ++s) X[s] = 0.0;
         X[0] = 1.0;
-        const double h2 = 0.5 * dt, h6 = dt / 6.0;
+        const double h2 = __dmul_rn(0.5, dt), h6 = __ddiv_rn(dt, 6.0);
         for (int it = 0; it < nsteps; ++it) {
             rhs(X, kf, kr, d);                                   // k1
 #pragma unroll
-            for (int s = 0; s <= S; ++s) { a[s] = d[s]; T[s] = X[s] + h2 * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = d[s]; T[s] = fma(h2, d[s], X[s]); }
             rhs(T, kf, kr, d);                                   // k2
 #pragma unroll
-            for (int s = 0; s <= S; ++s) { a[s] += 2.0 * d[s]; T[s] = X[s] + h2 * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(h2, d[s], X[s]); }
             rhs(T, kf, kr, d);                                   // k3
 #pragma unroll
-            for (int s = 0; s <= S; ++s) { a[s] += 2.0 * d[s]; T[s] = X[s] + dt * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(dt, d[s], X[s]); }
             rhs(T, kf, kr, d);                                   // k4
 #pragma unroll
-            for (int s = 0; s <= S; ++s) X[s] += h6 * (a[s] + d[s]);
+            for (int s = 0; s <= S; ++s) X[s] = fma(h6, __dadd_rn(a[s], d[s]), X[s]);
         }
         return X[S];
     }
 };
 
-// Run-time S (any k): state in local memory.
+// Run-time S (any k): state in local memory.  Same frozen arithmetic as RK4Chain<S>.
 struct RK4ChainDyn {
     double dt;
     int nsteps;
@@ -136,25 +162,25 @@ struct RK4ChainDyn {
         double X[MAXS + 1], T[MAXS + 1], a[MAXS + 1], d[MAXS + 1];
         for (int s = 0; s <= S; ++s) X[s] = 0.0;
         X[0] = 1.0;
-        const double h2 = 0.5 * dt, h6 = dt / 6.0;
+        const double h2 = __dmul_rn(0.5, dt), h6 = __ddiv_rn(dt, 6.0);
         auto rhs = [&](const double *Y) {
             double prev = 0.0;
             for (int s = 0; s < S; ++s) {
-                double flux = x[s] * Y[s] - x[S + s] * Y[s + 1];
-                d[s] = prev - flux;
+                double flux = fma(x[s], Y[s], -__dmul_rn(x[S + s], Y[s + 1]));
+                d[s] = __dsub_rn(prev, flux);
                 prev = flux;
             }
             d[S] = prev;
         };
         for (int it = 0; it < nsteps; ++it) {
             rhs(X);
-            for (int s = 0; s <= S; ++s) { a[s] = d[s]; T[s] = X[s] + h2 * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = d[s]; T[s] = fma(h2, d[s], X[s]); }
             rhs(T);
-            for (int s = 0; s <= S; ++s) { a[s] += 2.0 * d[s]; T[s] = X[s] + h2 * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(h2, d[s], X[s]); }
             rhs(T);
-            for (int s = 0; s <= S; ++s) { a[s] += 2.0 * d[s]; T[s] = X[s] + dt * d[s]; }
+            for (int s = 0; s <= S; ++s) { a[s] = fma(2.0, d[s], a[s]); T[s] = fma(dt, d[s], X[s]); }
             rhs(T);
-            for (int s = 0; s <= S; ++s) X[s] += h6 * (a[s] + d[s]);
+            for (int s = 0; s <= S; ++s) X[s] = fma(h6, __dadd_rn(a[s], d[s]), X[s]);
         }
         return X[S];
     }
@@ -165,6 +191,69 @@ __host__ __device__ __forceinline__ void tile_coords(int id, int nt, int &tr, in
     int rowlen = nt;
     while (id >= rowlen) { id -= rowlen; --rowlen; ++tr; }
     tc = tr + id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalisation: the estimators of varsens/saltelli.py:577-622 on the sufficient statistics, same
+// operation order (E_2 over n; U and Grams over n-1; mixed normalisation is the reference's).
+// Called by every thread of ONE CTA (finalize_kernel, the peer-memory exchange kernel, the tail of the
+// fused kernel).  P = packed partial sums (vs_partials_len), res = result vector:
+// E_2[l] var_y[l] U_j[kl] U_nj[kl] sens[kl] sens_t[kl] sens_2[(kl)^2] sens_2n[(kl)^2]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gram_at(const double *G, int m, int p, int q) {
+    if (p > q) { int t = p; p = q; q = t; }
+    return G[(size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)];
+}
+
+__device__ __forceinline__ void finalize_body(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
+                              double *__restrict__ res) {
+    const int m = (2 + 2 * k) * l;
+    const double *G = P + 4 * l;
+    const int kl = k * l;
+    double *E2 = res, *var = res + l, *Uj = res + 2 * l, *Unj = Uj + kl, *sens = Unj + kl, *senst = sens + kl;
+    double *s2 = senst + kl, *s2n = s2 + (size_t)kl * kl;
+    __shared__ double sE2[64], sVar[64];
+    for (int o = threadIdx.x; o < l; o += blockDim.x) {
+        double e2 = gram_at(G, m, 0 * l + o, 1 * l + o) / n;                                  // :577
+        double tot = P[o] + P[l + o];
+        double v = (P[2 * l + o] + P[3 * l + o] - tot * tot / (2.0 * rows)) / (2.0 * rows - 1.0);   // :583 (ddof=1 over 2*rows values)
+        E2[o] = e2;
+        var[o] = v;
+        if (o < 64) { sE2[o] = e2; sVar[o] = v; }
+    }
+    __syncthreads();
+    auto e2_of = [&](int o) { return o < 64 ? sE2[o] : E2[o]; };
+    auto var_of = [&](int o) { return o < 64 ? sVar[o] : var[o]; };
+    for (int e = threadIdx.x; e < kl; e += blockDim.x) {
+        int j = e / l, o = e - j * l;
+        int iA = o, iB = l + o, iJ = (2 + j) * l + o, iN = (2 + k + j) * l + o;
+        double uj = gram_at(G, m, iA, iJ) / (n - 1.0);                                        // :591-593
+        uj += gram_at(G, m, iB, iN) / (n - 1.0);
+        uj /= 2.0;
+        double unj = gram_at(G, m, iA, iN) / (n - 1.0);                                       // :594-596
+        unj += gram_at(G, m, iB, iJ) / (n - 1.0);
+        unj /= 2.0;
+        Uj[e] = uj;
+        Unj[e] = unj;
+        sens[e] = (uj - e2_of(o)) / var_of(o);                                                // :608
+        senst[e] = 1.0 - ((unj - e2_of(o)) / var_of(o));                                      // :609
+    }
+    if (!second_order) return;
+    for (size_t e = threadIdx.x; e < (size_t)kl * kl; e += blockDim.x) {
+        int ia = (int)(e / kl), jb = (int)(e % kl);
+        int i = ia / l, a = ia - i * l, j = jb / l, b = jb - j * l;
+        int Ji = (2 + i) * l + a, Ni = (2 + k + i) * l + a, Jj = (2 + j) * l + b, Nj = (2 + k + j) * l + b;
+        double v2 = gram_at(G, m, Ni, Jj) + gram_at(G, m, Ji, Nj);                            // :612-613
+        v2 /= 2.0 * (n - 1.0);
+        v2 -= e2_of(b);
+        v2 /= var_of(b);
+        double v2n = gram_at(G, m, Ni, Nj) + gram_at(G, m, Ji, Jj);                           // :618-619
+        v2n /= 2.0 * (n - 1.0);
+        v2n -= e2_of(b);
+        v2n /= var_of(b);
+        s2[e] = v2;
+        s2n[e] = v2n;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

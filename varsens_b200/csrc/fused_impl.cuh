@@ -51,6 +51,46 @@ struct FusedConst {            // kernel parameter -> constant bank; indexed wit
     int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
 };
 
+// Everything the LAST CTA of the fused kernel does once all CTA partial sums are in HBM (one launch per step): fixed-order
+// combine, packed partial-sum vector, optional peer-memory all-reduce over NVLink, estimators, results to device and to
+// mapped host memory.  Also carries the arrival flags of a host permutation that is still being copied while the kernel runs.
+struct FusedTail {
+    double *blockpart;               // [gridDim.x][LROW] compact CTA partial sums
+    unsigned *ticket;                // CTA completion counter (reset by the last CTA)
+    double *partials;                // out: packed partial-sum vector (device) or nullptr
+    double *res_dev;                 // out: result vector (device) or nullptr          } mode >= 1
+    double *res_host;                // out: result vector + status + time stamps in mapped pinned host memory or nullptr
+    double n_total, rows_total;      // divisors of the estimators (saltelli.py:577,591-596; rows < n after NaN trimming)
+    int mode;                        // 0 = partial sums only, 1 = + estimators, 2 = + peer exchange + estimators
+    int world, rank;
+    unsigned epoch;
+    const uint64_t *peer_bufs, *peer_flags;     // device arrays [world]: every rank's exchange buffer / flag array as mapped here
+    unsigned long long timeout_ns;   // bounded wait for the peers
+    const unsigned long long *arrive;           // chunk c of the permutation is in HBM when *arrive >= arrive_base + c + 1
+    unsigned long long arrive_base;
+    int nchunk;
+    uint32_t chunk_end_batch[16];    // first 32-row batch (relative to i_begin) NOT covered by chunks 0..c
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // compile-time loop: fn(std::integral_constant<int, I>{}) for I in [0, N)
 template <int N, class Fn, int... I>
 __device__ __forceinline__ void static_for_impl(Fn &&fn, std::integer_sequence<int, I...>) {
@@ -615,20 +655,229 @@ __device__ __forceinline__ void for_each_tile(Fn &&fn) {
     }
 }
 
+// ---- compact CTA partial sums and the last-CTA tail ---------------------------------------------------------------
+// A CTA's partial sums are stored tile-major: tile t of the for_each_tile walk owns 64 doubles, the C fragment of lane L
+// (row L/4, columns 2(L%4), 2(L%4)+1 of the 8x8 tile) at [t*64 + 2L, +1]; then the four shifted sums; padded to LROW.
+template <int NB, int HB, bool PM>
+__host__ __device__ constexpr int wsd_ntl() { return PM ? HB * (HB + 1) : NB * (NB + 1) / 2; }
+template <int NB, int HB, bool PM>
+__host__ __device__ constexpr int wsd_lrow() { return wsd_ntl<NB, HB, PM>() * 64 + 8; }
+
+// dense entry (x, y) (padded coordinates, either order) of the combined CTA sums D
+template <int NB, int HB, bool PM>
+__device__ __forceinline__ double dense_at(const double *__restrict__ D, int x, int y) {
+    const int lo = x < y ? x : y, hi = x < y ? y : x;
+    int P = lo >> 3, Q = hi >> 3, t;
+    if constexpr (PM) {
+        const int h = P / HB;
+        P -= h * HB;
+        Q -= h * HB;
+        t = h * (HB * (HB + 1) / 2) + P * HB - P * (P - 1) / 2 + (Q - P);
+    } else {
+        t = P * NB - P * (P - 1) / 2 + (Q - P);
+    }
+    return D[t * 64 + (lo & 7) * 8 + (hi & 7)];
+}
+
+// Entry e of the packed upper triangle of G (v = (A, B, J_0.., N_0..), include/varsens_b200.h) from the combined CTA sums.
+// Paired layout (Grams of w = (P, A, B) and u = (M, A, B), HS coordinates each): first-order entries are exact recombinations
+// (A.J_j = (A.P_j - A.M_j)/2, A.N_j = (A.P_j + A.M_j)/2); the J/N blocks come out symmetrised,
+//   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2,   G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
+// which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).
+template <int K, int NB, int HB, bool PM>
+__device__ __forceinline__ double packed_entry(const double *__restrict__ D, int e) {
+    constexpr int m = 2 + 2 * K;
+    int p = 0, rowlen = m, rem = e;
+    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
+    const int q = p + rem;
+    if constexpr (!PM) {
+        return dense_at<NB, HB, PM>(D, p, q);
+    } else {
+        constexpr int HS = 8 * HB;
+        auto Dd = [&](int x, int y) { return dense_at<NB, HB, PM>(D, x, y); };
+        if (q < 2) return Dd(K + p, K + q);                           // A.A, A.B, B.B (w triangle)
+        if (p < 2) {
+            const bool qn = q >= 2 + K;
+            const int j = qn ? q - 2 - K : q - 2;
+            const double ap = Dd(j, K + p), am = Dd(HS + j, HS + K + p);
+            return 0.5 * (qn ? ap + am : ap - am);
+        }
+        const bool pn = p >= 2 + K, qn = q >= 2 + K;
+        const int i = pn ? p - 2 - K : p - 2, j = qn ? q - 2 - K : q - 2;
+        const double pp = Dd(i, j), mm = Dd(HS + i, HS + j);
+        return 0.25 * (pn == qn ? pp + mm : pp - mm);
+    }
+}
+
+constexpr int TAIL_PARTS = 8;
+template <int K, int NB, int HB, bool PM>
+__host__ __device__ constexpr size_t wsd_tail_smem_doubles() {
+    constexpr int LROW = wsd_lrow<NB, HB, PM>();
+    constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
+    return (size_t)TAIL_PARTS * LROW + LROW + 2 * (size_t)(plen + 4) + rlen + 8;
+}
+
+// Runs in the last CTA to finish (all threads).  smem: dynamic shared memory of the kernel, free for reuse.
+template <int K, int NB, int HB, bool PM>
+__device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__restrict__ smem) {
+    constexpr int LROW = wsd_lrow<NB, HB, PM>();
+    constexpr int NTL = wsd_ntl<NB, HB, PM>();
+    constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
+    double *ps = smem;                                     // [TAIL_PARTS][LROW]
+    double *D = ps + (size_t)TAIL_PARTS * LROW;            // [LROW]
+    double *Pk = D + LROW;                                 // [plen] packed partial sums of this rank
+    double *Pr = Pk + plen + 4;                            // [plen] reduced over ranks (mode 2)
+    double *R = Pr + plen + 4;                             // [rlen] results
+    const int tid = threadIdx.x, nthr = blockDim.x, nb = gridDim.x;
+    const unsigned long long t0 = globaltimer_ns();
+    // 1. CTA rows -> D, fixed order: TAIL_PARTS contiguous ranges of CTAs summed in CTA order, then the parts in part order
+    {
+        constexpr int L2 = LROW / 2;
+        const int per = (nb + TAIL_PARTS - 1) / TAIL_PARTS;
+        for (int task = tid; task < TAIL_PARTS * L2; task += nthr) {
+            const int part = task / L2, c2 = task - part * L2;
+            int b = part * per;
+            const int b1 = (b + per < nb) ? b + per : nb;
+            const double2 *src = reinterpret_cast<const double2 *>(tail.blockpart) + c2;
+            double2 acc = make_double2(0.0, 0.0);
+            for (; b + 4 <= b1; b += 4) {
+                double2 v0 = __ldcg(src + (size_t)(b + 0) * L2), v1 = __ldcg(src + (size_t)(b + 1) * L2);
+                double2 v2 = __ldcg(src + (size_t)(b + 2) * L2), v3 = __ldcg(src + (size_t)(b + 3) * L2);
+                acc.x += v0.x; acc.y += v0.y;
+                acc.x += v1.x; acc.y += v1.y;
+                acc.x += v2.x; acc.y += v2.y;
+                acc.x += v3.x; acc.y += v3.y;
+            }
+            for (; b < b1; ++b) {
+                double2 v = __ldcg(src + (size_t)b * L2);
+                acc.x += v.x; acc.y += v.y;
+            }
+            reinterpret_cast<double2 *>(ps + (size_t)part * LROW)[c2] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < LROW; e += nthr) {
+            double v = 0.0;
+#pragma unroll
+            for (int part = 0; part < TAIL_PARTS; ++part) v += ps[(size_t)part * LROW + e];
+            D[e] = v;
+        }
+        __syncthreads();
+    }
+    // 2. packed partial-sum vector
+    for (int e = tid; e < plen; e += nthr) {
+        const double v = e < 4 ? D[NTL * 64 + e] : packed_entry<K, NB, HB, PM>(D, e - 4);
+        Pk[e] = v;
+        if (tail.partials) tail.partials[e] = v;
+    }
+    __syncthreads();
+    if (tail.mode == 0) return;
+    const unsigned long long t1 = globaltimer_ns();
+    unsigned long long t2 = t1, t3 = t1;
+    const double *Pfin = Pk;
+    __shared__ unsigned timed_out;
+    if (tid == 0) timed_out = 0u;
+    if (tail.mode == 2) {
+        // 3. all-reduce over NVLink peer memory: my vector -> slot `rank` of every rank's buffer (one warp per peer, remote
+        //    stores), flag, wait for everybody's flag (bounded), sum the slots in rank order (same bits on every rank).
+        const int set = (int)(tail.epoch & 1u), world = tail.world, rank = tail.rank;
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
+        for (int r = warp; r < world; r += nwarp) {
+            double *dst = reinterpret_cast<double *>(tail.peer_bufs[r]) + ((size_t)set * world + rank) * plen;
+            for (int e = lane; e < plen; e += 32) dst[e] = Pk[e];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < world)
+            st_release_sys_u32(reinterpret_cast<unsigned *>(tail.peer_flags[tid]) + (size_t)set * world + rank, tail.epoch);
+        t2 = globaltimer_ns();
+        if (tid < world) {
+            const unsigned *fl = reinterpret_cast<const unsigned *>(tail.peer_flags[rank]) + (size_t)set * world + tid;
+            while (ld_acquire_sys_u32(fl) != tail.epoch) {
+                if (globaltimer_ns() - t2 > tail.timeout_ns) { timed_out = 1u; break; }
+                __nanosleep(64);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        t3 = globaltimer_ns();
+        const double *slots = reinterpret_cast<const double *>(tail.peer_bufs[rank]) + (size_t)set * world * plen;
+        for (int e = tid; e < plen; e += nthr) {
+            double v = 0.0;
+            for (int r = 0; r < world; ++r) v += __ldcv(slots + (size_t)r * plen + e);
+            Pr[e] = v;
+        }
+        __syncthreads();
+        Pfin = Pr;
+    }
+    // 4. estimators
+    finalize_body(K, 1, tail.n_total, tail.rows_total, Pfin, 1, R);
+    __syncthreads();
+    for (int e = tid; e < rlen; e += nthr) {
+        const double v = R[e];
+        if (tail.res_dev) tail.res_dev[e] = v;
+        if (tail.res_host) tail.res_host[e] = v;
+    }
+    if (tail.res_host && tid == 0) {
+        double *x = tail.res_host + rlen;
+        x[0] = timed_out ? 1.0 : 0.0;
+        x[1] = (double)(t1 - t0);                       // combine + pack, ns
+        x[2] = (double)(t2 - t1);                       // peer stores + fence + flags
+        x[3] = (double)(t3 - t2);                       // wait for the peers
+        x[4] = (double)(globaltimer_ns() - t3);         // rank-order sum + estimators + result stores
+    }
+    __threadfence_system();
+}
+
+// Coordinate d of the Halton point m from the fixed-layout shared table (run-time d; used once per CTA for the shift).
+__device__ __forceinline__ uint32_t prime_rt(int d) {
+    uint32_t p = 2;
+#pragma unroll 1
+    for (int e = 0; e < d; ++e) {
+        for (++p;; ++p) {
+            bool pr = true;
+            for (uint32_t q = 2; q * q <= p; ++q)
+                if (p % q == 0) { pr = false; break; }
+            if (pr) break;
+        }
+    }
+    return p;
+}
+__device__ __forceinline__ double halton_coord_fixed(const double *__restrict__ terms, int d, uint32_t m) {
+    if (d == 0) return (double)__brev(m) * 2.3283064365386962890625e-10;
+    uint32_t off = 0, b = 2;
+#pragma unroll 1
+    for (int e = 1; e <= d; ++e) {
+        b = prime_rt(e);
+        if (e < d) off += b * (uint32_t)ndmax32(b);
+    }
+    const double *row = terms + off;
+    double x = 0.0;
+    while (m != 0u) {
+        const uint32_t q = m / b;
+        x = __dadd_rn(x, row[m - q * b]);
+        row += b;
+        m = q;
+    }
+    return x;
+}
+
 template <int K, class F, bool SEPARABLE, int EPS, int NBUF>
 __global__ void __launch_bounds__((EPS + 1) * WS_S * 32, 1)
-fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, const double *__restrict__ shift_ptr,
-                 double *__restrict__ blockpart) {
+fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, FusedTail tail) {
     constexpr int WS_E = EPS * WS_S;
     constexpr int M = 2 + 2 * K;
     constexpr bool PM = wsd_paired<K, F, SEPARABLE>();  // paired tile layout (see pm_pays)
     constexpr int HB = pm_hb<K>();
     constexpr int NB = PM ? 2 * HB : (M + 7) / 8;       // 8-wide blocks of a tile row
     constexpr int MPAD = NB * 8;
-    constexpr int NTL = PM ? HB * (HB + 1) : NB * (NB + 1) / 2;    // 8x8 tiles: two upper triangles / one
+    constexpr int NTL = wsd_ntl<NB, HB, PM>();          // 8x8 tiles: two upper triangles / one
+    constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int TILE = MPAD * YT_PITCH;               // doubles per Y tile
 
     extern __shared__ double smem[];
+    __shared__ double xs_sh[K];
+    __shared__ double shift_sh;
+    __shared__ unsigned last_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nterms = src.raw ? 0u : foff(K);
     double *terms = smem;
@@ -640,6 +889,22 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     if (threadIdx.x == 0) {
         *tokp = F::token;
         for (int b = 0; b < 2 * NBUF * WS_E; ++b) mbar_init(bars + b, 1);
+    }
+    __syncthreads();
+    // common shift of the variance sums, f(M_1[0]): every CTA (and every rank) derives the same bits from base row 0
+    if (threadIdx.x < K) {
+        const int d = threadIdx.x;
+        double p = src.raw ? src.raw[d] : halton_coord_fixed(terms, d, (uint32_t)src.start);
+        if (fc.scale_kind == VS_SCALE_LINEAR) p = __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);
+        else if (fc.scale_kind == VS_SCALE_POWER) p = __dmul_rn(fc.lb[d], pow(fc.wr[d], p));
+        xs_sh[d] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) x[c] = xs_sh[c];
+        shift_sh = f(x, F::token);
     }
     __syncthreads();
     auto full_bar = [&](int e, int slot) { return bars + (e * NBUF + slot); };
@@ -663,7 +928,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         if constexpr (EPS == 2) reg_inc<192>();          // 12 warps: S warpgroup 112, E warpgroups 192 registers per thread
 #endif
         const int e = warp - WS_S;
-        const double shift = *shift_ptr;
+        const double shift = shift_sh;
         const uint64_t cnt = count_of(e);
         uint64_t bt = (uint64_t)blockIdx.x * WS_E + e;
         // Phase alternation between the two E-warp teams (team = e / WS_S; every sub-partition has one warp of each).
@@ -679,6 +944,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         const uint64_t bars_total = 2 * count_of(0) + 1;              // count_of(0) is the largest batch count in the CTA
         uint64_t bars_done = 0;
         if (alternate && team == 1) { ebar(); ++bars_done; }
+        int chunk = 0;                                                // permutation chunks [0, chunk) are known to be in HBM
         for (uint64_t it = 0; it < cnt; ++it, bt += G) {
             const int slot = (int)(it % NBUF);
             double a[K], b[K];
@@ -686,6 +952,14 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
             const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 64;
             long long *trp = fc.trace + ((size_t)warp * 64 + (it < 64 ? it : 0)) * 4;
             if (tr_on) trp[0] = clock64();
+            if (tail.arrive && (chunk == 0 || bt >= (uint64_t)tail.chunk_end_batch[chunk - 1])) {
+                // host permutation still on its way: wait (warp-uniform) until the slice that holds this batch has landed
+                int need = chunk;
+                while (need + 1 < tail.nchunk && bt >= (uint64_t)tail.chunk_end_batch[need]) ++need;
+                const unsigned long long want = tail.arrive_base + (unsigned long long)need + 1ull;
+                while (ld_acquire_sys_u64(tail.arrive) < want) __nanosleep(200);
+                chunk = need + 1;
+            }
             if (fc.debug & 1) {
 #pragma unroll
                 for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
@@ -752,17 +1026,14 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         }
     }
 
-    // ---- combine: every S-warp drops its C fragments into a dense MPAD x MPAD image, summed in S-warp order ----
+    // ---- combine: every S-warp drops its C fragments into a compact tile-major image, summed in S-warp order ----
     __syncthreads();
-    double *img = smem;                                   // [WS_S][MPAD*MPAD] then [WS_E][4]
-    double *sums = img + (size_t)WS_S * MPAD * MPAD;
+    double *img = smem;                                   // [WS_S][NTL*64] then [WS_E][4]
+    double *sums = img + (size_t)WS_S * NTL * 64;
     if (warp < WS_S) {
-        double *mine = img + (size_t)warp * MPAD * MPAD;
-        for_each_tile<NB, HB, PM>([&](int t, int P, int Q) {
-            const int row = 8 * P + (lane >> 2), col = 8 * Q + 2 * (lane & 3);   // C fragment: (lane/4, 2*(lane%4)+{0,1})
-            mine[row * MPAD + col] = acc[t][0];
-            mine[row * MPAD + col + 1] = acc[t][1];
-        });
+        double2 *mine = reinterpret_cast<double2 *>(img + (size_t)warp * NTL * 64);
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) mine[t * 32 + lane] = make_double2(acc[t][0], acc[t][1]);
     } else {
         sA = warp_sum(sA); qA = warp_sum(qA); sB = warp_sum(sB); qB = warp_sum(qB);
         if (lane == 0) {
@@ -771,94 +1042,28 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         }
     }
     __syncthreads();
-    constexpr int PER_BLOCK = MPAD * MPAD + 4;
-    double *bp = blockpart + (size_t)blockIdx.x * PER_BLOCK;
-    for (int e = threadIdx.x; e < MPAD * MPAD; e += blockDim.x) {
-        const int row = e / MPAD, col = e % MPAD;
+    double *bp = tail.blockpart + (size_t)blockIdx.x * LROW;
+    for (int e = threadIdx.x; e < NTL * 64; e += blockDim.x) {
         double v = 0.0;
-        const bool computed = row / 8 <= col / 8 && (!PM || (row / 8) / HB == (col / 8) / HB);
-        if (computed) {
 #pragma unroll
-            for (int w = 0; w < WS_S; ++w) v += img[(size_t)w * MPAD * MPAD + e];
-        }
+        for (int w = 0; w < WS_S; ++w) v += img[(size_t)w * NTL * 64 + e];
         bp[e] = v;
     }
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < 8) {
         double v = 0.0;
-        for (int w = 0; w < WS_E; ++w) v += sums[w * 4 + threadIdx.x];
-        bp[MPAD * MPAD + threadIdx.x] = v;
+        if (threadIdx.x < 4)
+            for (int w = 0; w < WS_E; ++w) v += sums[w * 4 + threadIdx.x];
+        bp[NTL * 64 + threadIdx.x] = v;
     }
-}
-
-// Sum of one entry over the CTA partials by a whole warp: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree
-// (bit-reproducible for a given grid size; every lane returns the total).  The thread-per-entry form of these scatter
-// kernels took 30-50 us -- a serial chain of 148 strided loads per thread -- which is 5 % of an 8-GPU step.
-__device__ __forceinline__ double warp_sum_over_blocks(const double *__restrict__ p, size_t stride, int nblocks, int lane) {
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += p[(size_t)b * stride];
-    return warp_sum(s);
-}
-
-// CTA partials of fused_wsd_kernel (dense MPAD x MPAD image + 4 shifted sums) -> packed partial-sum vector.  One warp per entry.
-static __global__ void __launch_bounds__(256) dense_scatter_kernel(int m, int mpad, int nblocks, const double *__restrict__ blockpart,
-                                                                   double *__restrict__ partials) {
-    const size_t per_block = (size_t)mpad * mpad + 4;
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w < 4) {
-        const double v = warp_sum_over_blocks(blockpart + (size_t)mpad * mpad + w, per_block, nblocks, lane);
-        if (lane == 0) partials[w] = v;
-        return;
-    }
-    const int e = w - 4;
-    if (e >= m * (m + 1) / 2) return;
-    int p = 0, rowlen = m, rem = e;
-    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
-    const int q = p + rem;
-    const double v = warp_sum_over_blocks(blockpart + (size_t)p * mpad + q, per_block, nblocks, lane);
-    if (lane == 0) partials[4 + e] = v;
-}
-
-// CTA partials of the paired layout (fused_wsd_kernel with wsd_paired: Grams of w = (P, A, B) and u = (M, A, B), HS coordinates
-// each) -> packed partial-sum vector of v = (A, B, J_0.., N_0..).  First-order entries are exact recombinations
-// (A.J_j = (A.P_j - A.M_j)/2, A.N_j = (A.P_j + A.M_j)/2); the J/N blocks come out symmetrised:
-//   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2,   G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
-// which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).  One warp per entry.
-static __global__ void __launch_bounds__(256) pm_scatter_kernel(int K, int HS, int nblocks, const double *__restrict__ blockpart,
-                                                                double *__restrict__ partials) {
-    const int mpad = 2 * HS, m = 2 + 2 * K;
-    const size_t per_block = (size_t)mpad * mpad + 4;
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w < 4) {
-        const double v = warp_sum_over_blocks(blockpart + (size_t)mpad * mpad + w, per_block, nblocks, lane);
-        if (lane == 0) partials[w] = v;
-        return;
-    }
-    const int e = w - 4;
-    if (e >= m * (m + 1) / 2) return;
-    int p = 0, rowlen = m, rem = e;
-    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
-    const int q = p + rem;
-    auto D = [&](int x, int y) {                               // CTA sum of dense entry (min, max)
-        const int lo = x < y ? x : y, hi = x < y ? y : x;
-        return warp_sum_over_blocks(blockpart + (size_t)lo * mpad + hi, per_block, nblocks, lane);
-    };
-    double v;
-    if (q < 2) {
-        v = D(K + p, K + q);                                    // A.A, A.B, B.B (w triangle)
-    } else if (p < 2) {
-        const bool qn = q >= 2 + K;
-        const int j = qn ? q - 2 - K : q - 2;
-        const double ap = D(j, K + p), am = D(HS + j, HS + K + p);
-        v = 0.5 * (qn ? ap + am : ap - am);
-    } else {
-        const bool pn = p >= 2 + K, qn = q >= 2 + K;
-        const int i = pn ? p - 2 - K : p - 2, j = qn ? q - 2 - K : q - 2;
-        const double pp = D(i, j), mm = D(HS + i, HS + j);
-        v = 0.25 * (pn == qn ? pp + mm : pp - mm);
-    }
-    if (lane == 0) partials[4 + e] = v;
+    // ---- ticket: the last CTA to get here runs the tail (its result does not depend on WHICH CTA that is) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_sh = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!last_sh) return;
+    __threadfence();
+    fused_tail<K, NB, HB, PM>(tail, smem);
+    if (threadIdx.x == 0) *tail.ticket = 0u;
 }
 
 // f(M_1[0]): the common shift for the variance sums (identical on every rank).
@@ -881,9 +1086,22 @@ __global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) 
     }
 }
 
+// kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
+//   1 = single-role warps, register-tile Gram (also the first-order-only kernel; separate shift / scatter launches)
+//   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp     (one launch per step)
+// default: 6, except k >= 20 where the 12-warp form (168 registers per thread, no spills) wins since the paired layout
+// lightened the S-warps (n = 2^24: 4.79 vs 5.06 ms; k <= 18: variant 6 is 1-13 % faster, tools/variant_sweep.py)
+template <int K>
+static int fused_variant_for(const vs_ctx *c, bool second) {
+    if (!second) return 1;
+    const int v = c->opt.fused_variant;
+    if (v == 1 || v == 5 || v == 6) return v;
+    return K >= 20 ? 5 : 6;
+}
+
 template <int K, class F, bool SECOND, bool SEPARABLE>
 static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &fc, const F &f, uint64_t i_begin, uint64_t i_end,
-                          double *partials) {
+                          double *partials, const FusedReq *req, bool *finalized) {
     constexpr int M = 2 + 2 * K;
     constexpr int T = SECOND ? gram_tile_for(M) : 2;
     constexpr int NT = (M + T - 1) / T;
@@ -894,43 +1112,72 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     const uint32_t nterms = src.raw ? 0u : foff(K);
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
-    // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
-    //   1 = single-role warps, register-tile Gram (also the first-order-only kernel)
-    //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp
-    // default: 6, except k >= 20 where the 12-warp form (168 registers per thread, no spills) wins since the paired layout
-    // lightened the S-warps (n = 2^24: 4.79 vs 5.06 ms; k <= 18: variant 6 is 1-13 % faster, tools/variant_sweep.py)
-    int variant = SECOND ? (K >= 20 ? 5 : 6) : 1;
-    if (const char *ev = getenv("VS_FUSED_VARIANT")) variant = SECOND ? atoi(ev) : 1;
+    const int variant = fused_variant_for<K>(c, SECOND);
+    *finalized = false;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
             constexpr bool PMk = wsd_paired<K, F, SEPARABLE>();
-            constexpr int NBk = PMk ? 2 * pm_hb<K>() : (M + 7) / 8, MPADk = NBk * 8;
+            constexpr int HBk = pm_hb<K>();
+            constexpr int NBk = PMk ? 2 * HBk : (M + 7) / 8, MPADk = NBk * 8;
+            constexpr int LROWk = wsd_lrow<NBk, HBk, PMk>(), NTLk = wsd_ntl<NBk, HBk, PMk>();
+            constexpr int RLEN = 2 + 4 * K + 2 * K * K;
             const int eps = variant == 6 ? 3 : 2;
             uint64_t wantd = (nbatch + eps * WS_S - 1) / (eps * WS_S);
             int gridd = (int)(wantd < (uint64_t)c->sm_count ? wantd : (uint64_t)c->sm_count);
             if (gridd < 1) gridd = 1;
-            const size_t per_block = (size_t)MPADk * MPADk + 4;
-            VS_TRY(ensure(c, c->block_buf, (size_t)gridd * per_block * sizeof(double)));
-            VS_TRY(ensure(c, c->misc_buf, 64));
-            shift_kernel<K, F><<<1, (K + 31) / 32 * 32, 0, c->stream>>>(src, fc, f, (double *)c->misc_buf.p);
-            c->launches++;
+            VS_TRY(ensure(c, c->block_buf, (size_t)gridd * LROWk * sizeof(double)));
+            if (!c->ticket_buf.p) {
+                VS_TRY(ensure(c, c->ticket_buf, 256));
+                VS_CUDA(cudaMemsetAsync(c->ticket_buf.p, 0, 256, c->stream));
+            }
+            FusedTail tail{};
+            tail.blockpart = (double *)c->block_buf.p;
+            tail.ticket = (unsigned *)c->ticket_buf.p;
+            tail.partials = partials;
+            tail.mode = req ? req->mode : 0;
+            if (tail.mode >= 1) {
+                VS_TRY(ensure(c, c->res_buf, (size_t)RLEN * sizeof(double)));
+                VS_TRY(ensure_host_res(c, (size_t)RLEN + HOST_RES_EXTRA));
+                tail.res_dev = (double *)c->res_buf.p;
+                tail.res_host = c->host_res;
+                tail.n_total = (double)req->n_total;
+                tail.rows_total = (double)req->rows_total;
+                tail.world = req->world;
+                tail.rank = req->rank;
+                tail.epoch = req->epoch;
+                tail.peer_bufs = req->peer_bufs_dev;
+                tail.peer_flags = req->peer_flags_dev;
+                tail.timeout_ns = (unsigned long long)c->opt.p2p_timeout_ms * 1000000ull;
+            }
+            if (req && req->arrive_dev) {
+                tail.arrive = req->arrive_dev;
+                tail.arrive_base = req->arrive_base;
+                tail.nchunk = req->nchunk;
+                for (int ch = 0; ch < 16; ++ch) tail.chunk_end_batch[ch] = req->chunk_end_batch[ch];
+            }
             size_t smem_run = ((size_t)nterms + 1 + 2 * eps * WS_S + (size_t)eps * WS_S * MPADk * YT_PITCH) * sizeof(double);
-            size_t smem_red = ((size_t)WS_S * MPADk * MPADk + 4 * eps * WS_S) * sizeof(double);
+            size_t smem_red = ((size_t)WS_S * NTLk * 64 + 4 * eps * WS_S) * sizeof(double);
+            size_t smem_tail = wsd_tail_smem_doubles<K, NBk, HBk, PMk>() * sizeof(double);
             size_t smem = smem_run > smem_red ? smem_run : smem_red;
+            if (smem_tail > smem) smem = smem_tail;
             VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
             auto kern = variant == 6 ? fused_wsd_kernel<K, F, SEPARABLE, 3, 1> : fused_wsd_kernel<K, F, SEPARABLE, 2, 1>;
-            VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static size_t smem_set[64][2] = {};                  // per instantiation and device: set the attribute once per size
+            if (c->device >= 64 || smem_set[c->device][variant == 6] < smem) {
+                VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (c->device < 64) smem_set[c->device][variant == 6] = smem;
+            }
             time_begin(c);
-            kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, (const double *)c->misc_buf.p,
-                                                                    (double *)c->block_buf.p);
+            kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, tail);
             time_end(c);
             c->launches++;
             VS_CUDA(cudaGetLastError());
+            *finalized = tail.mode >= 1;
             if (fc.trace) {                                  // profiling only: dump CTA 0's clock stamps
                 std::vector<long long> h(16 * 64 * 4);
                 VS_CUDA(cudaMemcpyAsync(h.data(), fc.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
                 VS_CUDA(cudaStreamSynchronize(c->stream));
-                if (FILE *fp = fopen(getenv("VS_TRACE"), "w")) {
+                if (FILE *fp = fopen(c->opt.trace.c_str(), "w")) {
                     for (int w = 0; w < 16; ++w)
                         for (int i = 0; i < 64; ++i) {
                             const long long *r = &h[((size_t)w * 64 + i) * 4];
@@ -939,18 +1186,11 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
                     fclose(fp);
                 }
             }
-            const int plen = (int)vs_partials_len(K, 1);
-            VS_CUDA(cudaMemsetAsync(partials, 0, (size_t)plen * sizeof(double), c->stream));
-            if constexpr (PMk)
-                pm_scatter_kernel<<<(M * (M + 1) / 2 + 4 + 7) / 8, 256, 0, c->stream>>>(K, MPADk / 2, gridd, (const double *)c->block_buf.p, partials);
-            else
-                dense_scatter_kernel<<<(M * (M + 1) / 2 + 4 + 7) / 8, 256, 0, c->stream>>>(M, MPADk, gridd, (const double *)c->block_buf.p,
-                                                                                       partials);
-            c->launches++;
-            VS_CUDA(cudaGetLastError());
             return VS_OK;
         }
     }
+    VS_REQUIRE(partials, VS_ERR_ARG, "this fused kernel variant needs a partial-sum buffer");
+    VS_REQUIRE(!(req && req->arrive_dev), VS_ERR_UNSUPPORTED, "this fused kernel variant cannot poll permutation chunks");
     const int ewarps = FUSED_WARPS;
     uint64_t want = (nbatch + ewarps - 1) / ewarps;
     int grid = (int)(want < (uint64_t)c->sm_count ? want : (uint64_t)c->sm_count);
@@ -983,7 +1223,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
 template <int K>
 static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedConst<K> &fc) {
     fc.scale_kind = s.kind;
-    fc.debug = getenv("VS_DEBUG_SKIP") ? atoi(getenv("VS_DEBUG_SKIP")) : 0;
+    fc.debug = c->opt.debug_skip;
     const double *h = s.host;                                   // lb | wr
     for (int d = 0; d < K; ++d) {
         fc.lb[d] = s.kind != VS_SCALE_IDENTITY ? h[d] : 0.0;
@@ -994,8 +1234,8 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
     }
     fc.small_index = 0;
     fc.trace = nullptr;
-    fc.alternate = getenv("VS_ALTERNATE") ? atoi(getenv("VS_ALTERNATE")) : 0;
-    if (getenv("VS_TRACE")) {
+    fc.alternate = c->opt.alternate;
+    if (!c->opt.trace.empty()) {
         VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
         VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));
         fc.trace = (long long *)c->dir_buf.p;
@@ -1019,7 +1259,7 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
 
 template <int K>
 static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin, uint64_t i_end,
-                      int flags, double *partials) {
+                      int flags, double *partials, const FusedReq *req, bool *finalized) {
     FusedConst<K> fc;
     VS_TRY(fill_const<K>(c, src, s, fc));
     const bool second = flags & VS_FLAG_SECOND_ORDER, sep = flags & VS_FLAG_SEPARABLE;
@@ -1029,21 +1269,28 @@ static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const 
         f.C = 1.0;
         for (int d = 0; d < K; ++d) { f.a[d] = hp[d]; f.C *= hp[K + d]; }
         if (second) {
-            if (sep) return launch_fused_t<K, GFunctionReg<K>, true, true>(c, src, fc, f, i_begin, i_end, partials);
-            return launch_fused_t<K, GFunctionReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials);
+            if (sep) return launch_fused_t<K, GFunctionReg<K>, true, true>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
+            return launch_fused_t<K, GFunctionReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
         }
-        if (sep) return launch_fused_t<K, GFunctionReg<K>, false, true>(c, src, fc, f, i_begin, i_end, partials);
-        return launch_fused_t<K, GFunctionReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials);
+        if (sep) return launch_fused_t<K, GFunctionReg<K>, false, true>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
+        return launch_fused_t<K, GFunctionReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
     }
     if constexpr (K == 3) {
         if (o.id == VS_OBJ_ISHIGAMI) {
             IshigamiReg<K> f{hp[0], hp[1]};
-            if (second) return launch_fused_t<K, IshigamiReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials);
-            return launch_fused_t<K, IshigamiReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials);
+            if (second) return launch_fused_t<K, IshigamiReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
+            return launch_fused_t<K, IshigamiReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
         }
     }
     set_error("objective %d has no fused kernel for k=%d", o.id, K);
     return VS_ERR_UNSUPPORTED;
+}
+
+// The one-launch step (estimators / peer exchange / chunk flags in the kernel's tail) exists for the warp-specialised variants.
+template <int K>
+static bool tail_supported_k(const vs_ctx *c, int flags) {
+    const int v = fused_variant_for<K>(c, (flags & VS_FLAG_SECOND_ORDER) != 0);
+    return v == 5 || v == 6;
 }
 
 }  // namespace vs

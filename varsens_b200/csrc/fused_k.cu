@@ -9,7 +9,8 @@
 
 namespace vs {
 int VS_CAT(launch_fused_k, VS_FUSED_K)(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
-                                       uint64_t i_end, int flags, double *partials) {
-    return dispatch_k<VS_FUSED_K>(c, src, s, o, i_begin, i_end, flags, partials);
+                                       uint64_t i_end, int flags, double *partials, const FusedReq *req, bool *finalized) {
+    return dispatch_k<VS_FUSED_K>(c, src, s, o, i_begin, i_end, flags, partials, req, finalized);
 }
+bool VS_CAT(fused_tail_k, VS_FUSED_K)(const vs_ctx *c, int flags) { return tail_supported_k<VS_FUSED_K>(c, flags); }
 }  // namespace vs

@@ -1,6 +1,7 @@
 // Context, error reporting, scratch management and host-built tables.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vs_internal.cuh"
@@ -53,6 +54,44 @@ int stage_in(vs_ctx *c, DevBuf &scratch, const void *p, int mem, size_t bytes, c
     return VS_OK;
 }
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+void load_options(Options &o) {
+    o = Options();
+    o.fused_variant = env_int("VS_FUSED_VARIANT", 0);
+    o.no_pipeline = env_int("VS_NO_PIPELINE", 0);
+    o.alternate = env_int("VS_ALTERNATE", 0);
+    o.debug_skip = env_int("VS_DEBUG_SKIP", 0);
+    if (const char *t = getenv("VS_TRACE")) o.trace = t;
+    o.gram_mma = env_int("VS_GRAM_MMA", -1);
+    o.gram_st = env_int("VS_GRAM_ST", 0);
+    o.gram_rc = env_int("VS_GRAM_RC", 0);
+    o.gram_stages = env_int("VS_GRAM_STAGES", 0);
+    o.gram_hint = env_int("VS_GRAM_HINT", 0x989680);
+    o.gram_debug = env_int("VS_GRAM_DEBUG", 0);
+    o.p2p_timeout_ms = env_int("VS_P2P_TIMEOUT_MS", 10000);
+    o.halton_mode = env_int("VS_HALTON_MODE", 0);
+}
+
+// Mapped pinned host memory the tail of the fused kernel writes its results to (no device-to-host copy call on the step).
+int ensure_host_res(vs_ctx *c, size_t doubles) {
+    if (c->host_res && c->host_res_cap >= doubles) return VS_OK;
+    if (c->host_res) {
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        VS_CUDA(cudaFreeHost(c->host_res));
+        c->host_res = nullptr;
+        c->host_res_cap = 0;
+    }
+    size_t want = doubles < 4096 ? 4096 : doubles;
+    VS_CUDA(cudaHostAlloc((void **)&c->host_res, want * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->host_res, 0, want * sizeof(double));
+    c->host_res_cap = want;
+    return VS_OK;
+}
+
 bool capturing(vs_ctx *c) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(c->stream, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
@@ -90,21 +129,30 @@ static void digit_counts(const std::vector<uint32_t> &bases, uint64_t max_index,
     }
 }
 
-// The one place that fixes the generator's fp64 arithmetic: term = (double)digit / (double)b^(j+1),
-// with b^(j+1) accumulated as ghalton does (bp *= b; exact for every index range we accept).
-static void build_terms(const std::vector<uint32_t> &bases, const std::vector<uint32_t> &nd, std::vector<uint32_t> &off,
+// The one place that fixes the generator's fp64 arithmetic (enum vs_halton_mode, include/varsens_b200.h).  Default: term =
+// (double)digit / (double)b^(j+1), with b^(j+1) accumulated as ghalton does (bp *= b; exact for every index range we
+// accept).  The kernels only add table entries in digit order, so re-pointing them at a different ghalton build -- should a
+// real install ever disagree with the restatement, tests/golden/make_ghalton_golden.py -- is choosing another mode here.
+static void build_terms(const std::vector<uint32_t> &bases, const std::vector<uint32_t> &nd, int mode, std::vector<uint32_t> &off,
                         std::vector<double> &terms) {
     off.resize(bases.size());
     terms.clear();
     for (size_t d = 0; d < bases.size(); ++d) {
         off[d] = (uint32_t)terms.size();
         volatile double bp = (double)bases[d];
+        volatile double ib = 1.0 / (double)bases[d];
+        volatile double f = ib;                                   // RUNNING_RECIPROCAL: f_j
         for (uint32_t j = 0; j < nd[d]; ++j) {
+            volatile double rbp = 1.0 / bp;                       // RECIPROCAL: 1 / b^(j+1)
             for (uint32_t digit = 0; digit < bases[d]; ++digit) {
-                volatile double q = (double)digit / bp;
+                volatile double q;
+                if (mode == VS_HALTON_RECIPROCAL) q = (double)digit * rbp;
+                else if (mode == VS_HALTON_RUNNING_RECIPROCAL) q = (double)digit * f;
+                else q = (double)digit / bp;
                 terms.push_back((double)q);
             }
             bp = bp * (double)bases[d];
+            f = f * ib;
         }
     }
 }
@@ -116,14 +164,15 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
     first_primes(k, bases);
     digit_counts(bases, max_index, nd);
     HaltonCache &hc = c->halton;
-    bool hit = hc.blob && hc.k == k && hc.ndigits.size() == nd.size();
+    const int mode = c->opt.halton_mode;
+    bool hit = hc.blob && hc.k == k && hc.mode == mode && hc.ndigits.size() == nd.size();
     if (hit)
         for (size_t d = 0; d < nd.size(); ++d)
             if (hc.ndigits[d] < nd[d]) { hit = false; break; }
     if (!hit) {
         std::vector<uint32_t> off;
         std::vector<double> terms;
-        build_terms(bases, nd, off, terms);
+        build_terms(bases, nd, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, off, terms);
         std::vector<uint64_t> magic(k);
         for (int d = 0; d < k; ++d) magic[d] = (~0ull) / bases[d] + 1ull;   // floor((2^64-1)/b)+1 == floor(2^64/b)+1 for b not a power of 2; b=2 unused
         size_t nb_terms = terms.size() * sizeof(double), nb_magic = (size_t)k * 8, nb_u32 = (size_t)k * 4;
@@ -148,8 +197,10 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         hc.dev.off = (const uint32_t *)p;
         hc.dev.total_terms = (uint32_t)terms.size();
         hc.k = k;
+        hc.mode = mode;
         hc.ndigits = nd;
     }
+    hc.dev.mode = mode;
     *out = hc.dev;
     return VS_OK;
 }
@@ -285,6 +336,8 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out) {
     c->stream = c->own_stream;
     VS_CUDA(cudaEventCreate(&c->ev0));
     VS_CUDA(cudaEventCreate(&c->ev1));
+    VS_CUDA(cudaHostAlloc((void **)&c->host_seq, 64 * sizeof(unsigned long long), cudaHostAllocPortable));
+    load_options(c->opt);
     *out = c;
     return VS_OK;
 }
@@ -294,7 +347,9 @@ extern "C" int vs_ctx_destroy(vs_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
-    DevBuf *bufs[] = {&c->peer_buf, &c->pipe_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
+    if (c->host_res) cudaFreeHost(c->host_res);
+    if (c->host_seq) cudaFreeHost(c->host_seq);
+    DevBuf *bufs[] = {&c->ticket_buf, &c->peer_buf, &c->pipe_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
                       &c->part_buf,  &c->block_buf, &c->res_buf, &c->dir_buf, &c->misc_buf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -313,6 +368,12 @@ extern "C" int vs_ctx_set_stream(vs_ctx *c, void *stream) {
     VS_CUDA(cudaSetDevice(c->device));
     VS_CUDA(cudaStreamSynchronize(c->stream));
     c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return VS_OK;
+}
+
+extern "C" int vs_ctx_reload_env(vs_ctx *c) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    load_options(c->opt);
     return VS_OK;
 }
 
@@ -342,14 +403,28 @@ extern "C" int vs_halton_bases(int k, uint32_t *bases) {
     return VS_OK;
 }
 
+extern "C" int vs_ctx_set_halton_mode(vs_ctx *c, int mode) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    VS_REQUIRE(mode >= VS_HALTON_DIVIDE && mode <= VS_HALTON_HORNER, VS_ERR_ARG, "unknown Halton mode %d", mode);
+    c->opt.halton_mode = mode;
+    return VS_OK;
+}
+
 extern "C" int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offsets, double *terms,
                                uint64_t capacity, uint64_t *count) {
+    return vs_halton_terms_mode(k, max_index, VS_HALTON_DIVIDE, ndigits, offsets, terms, capacity, count);
+}
+
+extern "C" int vs_halton_terms_mode(int k, uint64_t max_index, int mode, uint32_t *ndigits, uint32_t *offsets, double *terms,
+                                    uint64_t capacity, uint64_t *count) {
     VS_REQUIRE(k > 0 && count, VS_ERR_ARG, "bad arguments");
+    VS_REQUIRE(mode >= VS_HALTON_DIVIDE && mode <= VS_HALTON_RUNNING_RECIPROCAL, VS_ERR_UNSUPPORTED,
+               "Halton mode %d has no term table", mode);
     std::vector<uint32_t> bases, nd, off;
     std::vector<double> t;
     first_primes(k, bases);
     digit_counts(bases, max_index, nd);
-    build_terms(bases, nd, off, t);
+    build_terms(bases, nd, mode, off, t);
     *count = t.size();
     if (ndigits) memcpy(ndigits, nd.data(), sizeof(uint32_t) * k);
     if (offsets) memcpy(offsets, off.data(), sizeof(uint32_t) * k);

@@ -8,7 +8,8 @@ namespace vs {
 
 #define VS_DECLARE(KK)                                                                                                         \
     int launch_fused_k##KK(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin, \
-                           uint64_t i_end, int flags, double *partials);
+                           uint64_t i_end, int flags, double *partials, const FusedReq *req, bool *finalized);          \
+    bool fused_tail_k##KK(const vs_ctx *c, int flags);
 VS_FUSED_K_LIST(VS_DECLARE)
 #undef VS_DECLARE
 
@@ -26,10 +27,20 @@ bool fused_supported(int k, int objective, int flags) {
     }
 }
 
-int launch_fused(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
-                 uint64_t i_end, int flags, double *partials) {
+bool fused_tail_supported(vs_ctx *c, int k, int objective, int flags) {
+    if (!fused_supported(k, objective, flags)) return false;
     switch (k) {
-#define VS_CASE(KK) case KK: return launch_fused_k##KK(c, src, s, o, i_begin, i_end, flags, partials);
+#define VS_CASE(KK) case KK: return fused_tail_k##KK(c, flags);
+        VS_FUSED_K_LIST(VS_CASE)
+#undef VS_CASE
+    }
+    return false;
+}
+
+int launch_fused(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
+                 uint64_t i_end, int flags, double *partials, const FusedReq *req, bool *finalized) {
+    switch (k) {
+#define VS_CASE(KK) case KK: return launch_fused_k##KK(c, src, s, o, i_begin, i_end, flags, partials, req, finalized);
         VS_FUSED_K_LIST(VS_CASE)
 #undef VS_CASE
     }

@@ -351,8 +351,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
                     double *partials, bool *handled) {
     *handled = false;
     if (l != 1 || (rows & 1) || (reinterpret_cast<uintptr_t>(fvals) & 15) || rows == 0) return VS_OK;
-    if (const char *ev = getenv("VS_GRAM_MMA"))
-        if (atoi(ev) == 0) return VS_OK;
+    if (c->opt.gram_mma == 0) return VS_OK;
     MmaGeom g{};
     g.m = 2 + 2 * k;
     g.nb = (g.m + 7) / 8;
@@ -380,7 +379,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
         }
         if (best == 0.0) return VS_OK;            // more super-tiles than the tables hold: register-tile kernel
     }
-    if (const char *ev = getenv("VS_GRAM_ST")) { int v = atoi(ev); if (multi && (v == 2 || v == 4)) ST = v; }      // tuning switch
+    if (multi && (c->opt.gram_st == 2 || c->opt.gram_st == 4)) ST = c->opt.gram_st;                  // tuning switch (VS_GRAM_ST)
     const bool guard = multi || !g.second || g.nb != ST;
     g.nsb = (g.nb + ST - 1) / ST;
     g.nunits = g.second ? g.nsb * (g.nsb + 1) / 2 : g.nsb;
@@ -429,7 +428,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
     const size_t tail = ((size_t)g.upc * (8 * ST) * (8 * ST) + (size_t)g.rs * 16) * sizeof(double);
     // rows per chunk: as large as a ~60 KB stage allows (fewer, larger bulk copies and barrier round trips), ring of 3-6 stages
     int rc_cap = 256;
-    if (const char *ev = getenv("VS_GRAM_RC")) rc_cap = atoi(ev);                            // tuning switch
+    if (c->opt.gram_rc > 0) rc_cap = c->opt.gram_rc;                                          // tuning switch (VS_GRAM_RC)
     size_t smem = 0;
     g.nstage = 0;
     for (int rc : {256, 128, 64, 32}) {
@@ -446,9 +445,9 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
         break;
     }
     if (g.nstage < 2) return VS_OK;
-    if (const char *ev = getenv("VS_GRAM_STAGES")) { int v = atoi(ev); if (v >= 1 && v < g.nstage) g.nstage = v; }
-    g.hint = getenv("VS_GRAM_HINT") ? atoi(getenv("VS_GRAM_HINT")) : 0x989680;
-    g.debug = getenv("VS_GRAM_DEBUG") ? atoi(getenv("VS_GRAM_DEBUG")) : 0;
+    if (c->opt.gram_stages >= 1 && c->opt.gram_stages < g.nstage) g.nstage = c->opt.gram_stages;
+    g.hint = c->opt.gram_hint;
+    g.debug = c->opt.gram_debug;
     if (smem < MMA_BAR_DOUBLES * sizeof(double) + tail) smem = MMA_BAR_DOUBLES * sizeof(double) + tail;
     if (smem > avail) return VS_OK;
     int rc = VS_OK;

@@ -384,89 +384,48 @@ size_t result_len(int k, int l) {
     return 2 * (size_t)l + 4 * kl + 2 * kl * kl;
 }
 
-__device__ __forceinline__ double gram_at(const double *G, int m, int p, int q) {
-    if (p > q) { int t = p; p = q; q = t; }
-    return G[(size_t)p * m - (size_t)p * (p - 1) / 2 + (size_t)(q - p)];
-}
-
-__device__ void finalize_body(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
-                              double *__restrict__ res) {
-    const int m = (2 + 2 * k) * l;
-    const double *G = P + 4 * l;
-    const int kl = k * l;
-    double *E2 = res, *var = res + l, *Uj = res + 2 * l, *Unj = Uj + kl, *sens = Unj + kl, *senst = sens + kl;
-    double *s2 = senst + kl, *s2n = s2 + (size_t)kl * kl;
-    __shared__ double sE2[64], sVar[64];
-    for (int o = threadIdx.x; o < l; o += blockDim.x) {
-        double e2 = gram_at(G, m, 0 * l + o, 1 * l + o) / n;                                  // :577
-        double tot = P[o] + P[l + o];
-        double v = (P[2 * l + o] + P[3 * l + o] - tot * tot / (2.0 * rows)) / (2.0 * rows - 1.0);   // :583 (ddof=1 over 2*rows values)
-        E2[o] = e2;
-        var[o] = v;
-        if (o < 64) { sE2[o] = e2; sVar[o] = v; }
-    }
-    __syncthreads();
-    auto e2_of = [&](int o) { return o < 64 ? sE2[o] : E2[o]; };
-    auto var_of = [&](int o) { return o < 64 ? sVar[o] : var[o]; };
-    for (int e = threadIdx.x; e < kl; e += blockDim.x) {
-        int j = e / l, o = e - j * l;
-        int iA = o, iB = l + o, iJ = (2 + j) * l + o, iN = (2 + k + j) * l + o;
-        double uj = gram_at(G, m, iA, iJ) / (n - 1.0);                                        // :591-593
-        uj += gram_at(G, m, iB, iN) / (n - 1.0);
-        uj /= 2.0;
-        double unj = gram_at(G, m, iA, iN) / (n - 1.0);                                       // :594-596
-        unj += gram_at(G, m, iB, iJ) / (n - 1.0);
-        unj /= 2.0;
-        Uj[e] = uj;
-        Unj[e] = unj;
-        sens[e] = (uj - e2_of(o)) / var_of(o);                                                // :608
-        senst[e] = 1.0 - ((unj - e2_of(o)) / var_of(o));                                      // :609
-    }
-    if (!second_order) return;
-    for (size_t e = threadIdx.x; e < (size_t)kl * kl; e += blockDim.x) {
-        int ia = (int)(e / kl), jb = (int)(e % kl);
-        int i = ia / l, a = ia - i * l, j = jb / l, b = jb - j * l;
-        int Ji = (2 + i) * l + a, Ni = (2 + k + i) * l + a, Jj = (2 + j) * l + b, Nj = (2 + k + j) * l + b;
-        double v2 = gram_at(G, m, Ni, Jj) + gram_at(G, m, Ji, Nj);                            // :612-613
-        v2 /= 2.0 * (n - 1.0);
-        v2 -= e2_of(b);
-        v2 /= var_of(b);
-        double v2n = gram_at(G, m, Ni, Nj) + gram_at(G, m, Ji, Jj);                           // :618-619
-        v2n /= 2.0 * (n - 1.0);
-        v2n -= e2_of(b);
-        v2n /= var_of(b);
-        s2[e] = v2;
-        s2n[e] = v2n;
-    }
-}
-
 __global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, double rows, const double *__restrict__ P, int second_order,
                                                        double *__restrict__ res) {
     finalize_body(k, l, n, rows, P, second_order, res);
 }
 
-// Partial-sum all-reduce over NVLink peer memory fused with the finalisation (see vs_allreduce_finalize_p2p).
-// Single CTA.  bufs[r] / flgs[r] are rank r's exchange buffer / flag array as mapped into this process.
+// Partial-sum all-reduce over NVLink peer memory fused with the finalisation (see vs_allreduce_finalize_p2p); the stand-alone
+// form of the exchange the fused kernel runs in its tail (fused_impl.cuh: fused_tail), for partial sums that come from elsewhere
+// (two-phase path, user values).  Single CTA.  bufs[r] / flgs[r] are rank r's exchange buffer / flag array as mapped here.
+// res[rlen] = 1.0 if a peer did not show up within timeout_ns (the indices are then meaningless), else 0.0.
 __global__ void __launch_bounds__(256) p2p_reduce_finalize_kernel(int k, int l, double n, double rows, int world, int rank,
                                                                   const uint64_t *__restrict__ bufs, const uint64_t *__restrict__ flgs,
-                                                                  unsigned epoch, int plen, const double *__restrict__ mine,
-                                                                  int second_order, double *__restrict__ reduced, double *__restrict__ res) {
+                                                                  unsigned epoch, int plen, int rlen, unsigned long long timeout_ns,
+                                                                  const double *__restrict__ mine, int second_order,
+                                                                  double *__restrict__ reduced, double *__restrict__ res) {
     const int set = (int)(epoch & 1u);
-    // 1. my partial sums -> slot `rank` of every rank's buffer (remote stores over NVLink; the local one is a plain store)
-    for (int r = 0; r < world; ++r) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    __shared__ unsigned timed_out;
+    if (threadIdx.x == 0) timed_out = 0u;
+    // 1. my partial sums -> slot `rank` of every rank's buffer: one warp per peer (remote stores over NVLink, posted)
+    for (int r = warp; r < world; r += nwarp) {
         double *dst = reinterpret_cast<double *>(bufs[r]) + ((size_t)set * world + rank) * plen;
-        for (int e = threadIdx.x; e < plen; e += blockDim.x) dst[e] = mine[e];
+        for (int e = lane; e < plen; e += 32) dst[e] = mine[e];
     }
     __threadfence_system();
     __syncthreads();
-    // 2. publish: flag[set][rank] = epoch on every rank; then wait for everybody's flag in my own array
+    // 2. publish: flag[set][rank] = epoch on every rank; then wait (bounded) for everybody's flag in my own array
     if (threadIdx.x < world) {
-        volatile unsigned *f = reinterpret_cast<volatile unsigned *>(flgs[threadIdx.x]) + (size_t)set * world + rank;
-        *f = epoch;
+        unsigned *f = reinterpret_cast<unsigned *>(flgs[threadIdx.x]) + (size_t)set * world + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
     }
     if (threadIdx.x < world) {
-        volatile unsigned *f = reinterpret_cast<volatile unsigned *>(flgs[rank]) + (size_t)set * world + threadIdx.x;
-        while (*f != epoch) __nanosleep(100);
+        const unsigned *f = reinterpret_cast<const unsigned *>(flgs[rank]) + (size_t)set * world + threadIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { timed_out = 1u; break; }
+            __nanosleep(64);
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -479,14 +438,18 @@ __global__ void __launch_bounds__(256) p2p_reduce_finalize_kernel(int k, int l, 
     }
     __syncthreads();
     finalize_body(k, l, n, rows, reduced, second_order, res);
+    if (threadIdx.x == 0) res[rlen] = timed_out ? 1.0 : 0.0;
 }
 
 int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world, int rank, const uint64_t *peer_bufs_dev,
                                const uint64_t *peer_flags_dev, uint32_t epoch, const double *partials, int flags, double *res_dev) {
     const int plen = (int)vs_partials_len(k, l);
     VS_TRY(ensure(c, c->part_buf, (size_t)plen * sizeof(double)));
+    VS_REQUIRE(partials < (const double *)c->part_buf.p || partials >= (const double *)c->part_buf.p + plen, VS_ERR_ARG,
+               "partials_dev must not alias the exchange scratch");
     p2p_reduce_finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, (double)rows, world, rank, peer_bufs_dev, peer_flags_dev, epoch,
-                                                          plen, partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0,
+                                                          plen, (int)result_len(k, l), (unsigned long long)c->opt.p2p_timeout_ms * 1000000ull,
+                                                          partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0,
                                                           (double *)c->part_buf.p, res_dev);
     c->launches++;
     VS_CUDA(cudaGetLastError());

@@ -49,6 +49,7 @@ struct HaltonDev {
     const uint64_t *magic;
     const uint32_t *off;
     uint32_t total_terms;
+    int mode;               // enum vs_halton_mode (HORNER: the table is not used)
 };
 
 // scale.py:33 / :62 lowered: linear  -> p * w + lb   (w = ub - lb rounded on the host, as numpy does)
@@ -96,9 +97,39 @@ struct DevBuf {
 
 struct HaltonCache {
     int k = 0;
+    int mode = 0;
     std::vector<uint32_t> ndigits;
     HaltonDev dev{};
     void *blob = nullptr;
+};
+
+// Switches read from the environment ONCE, at vs_ctx_create (and again on vs_ctx_reload_env) -- never on a launch path.
+struct Options {
+    int fused_variant = 0;      // VS_FUSED_VARIANT  (0 = default choice per k)
+    int no_pipeline = 0;        // VS_NO_PIPELINE    host permutation: one copy, then the launch (no chunk flags)
+    int legacy_launch = 0;      // VS_LEGACY_LAUNCH  fused step as separate shift / fused / scatter / finalize launches
+    int alternate = 0;          // VS_ALTERNATE
+    int debug_skip = 0;         // VS_DEBUG_SKIP
+    std::string trace;          // VS_TRACE          file for CTA 0's clock stamps
+    int gram_mma = -1;          // VS_GRAM_MMA       (-1 = default)
+    int gram_st = 0, gram_rc = 0, gram_stages = 0, gram_hint = 0x989680, gram_debug = 0;
+    int p2p_timeout_ms = 10000; // VS_P2P_TIMEOUT_MS bounded wait for the peers' flags in the exchange
+    int halton_mode = 0;        // VS_HALTON_MODE    term-table arithmetic (enum vs_halton_mode)
+    int eg = 0;                 // reserved
+};
+
+// What the tail of the fused kernel has to do after the CTA partial sums are complete (host side of FusedTail).
+struct FusedReq {
+    int mode = 0;                       // 0 = partial sums only, 1 = + estimators, 2 = + peer-memory all-reduce + estimators
+    uint64_t n_total = 0, rows_total = 0;
+    int world = 1, rank = 0;
+    uint32_t epoch = 0;
+    const uint64_t *peer_bufs_dev = nullptr, *peer_flags_dev = nullptr;
+    // arrival of the permutation slices of a host permutation (chunk c is complete when *arrive_dev >= arrive_base + c + 1)
+    const unsigned long long *arrive_dev = nullptr;
+    unsigned long long arrive_base = 0;
+    int nchunk = 0;
+    uint32_t chunk_end_batch[16] = {0};
 };
 
 }  // namespace vs
@@ -118,6 +149,12 @@ struct vs_ctx {
     std::vector<double> scale_host, obj_host;
     std::vector<uint64_t> peer_tab;
     vs::DevBuf peer_buf;
+    vs::Options opt;
+    double *host_res = nullptr;          // mapped pinned host memory the fused kernel's tail writes the results to
+    size_t host_res_cap = 0;             // doubles
+    unsigned long long *host_seq = nullptr;   // pinned ring of sequence numbers (sources of the chunk-arrival flag copies)
+    unsigned long long seq = 0;          // last sequence number handed out
+    vs::DevBuf ticket_buf;               // ticket counter of the fused kernel's last-CTA tail + chunk-arrival flag
     int scale_kind_cached = -1, scale_k_cached = -1, obj_id_cached = -1;
     // scratch
     std::vector<cudaEvent_t> pipe_ev;    // chunk-arrival events of the pipelined host-permutation path
@@ -160,8 +197,14 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
                     double *partials, bool *handled);
 // kernels_fused.cu
 bool fused_supported(int k, int objective, int flags);
+// true if the kernel chosen for (k, objective, flags) runs the whole step in ONE launch (FusedReq modes 1/2, chunk flags)
+bool fused_tail_supported(vs_ctx *c, int k, int objective, int flags);
+// partials may be nullptr when req->mode >= 1.  *finalized reports whether the tail ran (results in c->host_res).
 int launch_fused(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin,
-                 uint64_t i_end, int flags, double *partials);
+                 uint64_t i_end, int flags, double *partials, const FusedReq *req, bool *finalized);
+int ensure_host_res(vs_ctx *c, size_t doubles);
+void load_options(Options &o);
+constexpr int HOST_RES_EXTRA = 32;      // doubles after the results: [0] status (0 ok, 1 peer time-out), [1..] tail time stamps (ns)
 // microbench.cu
 int launch_fp64_peak(vs_ctx *c, double *tflops);
 

@@ -7,14 +7,18 @@ import os
 
 
 def world():
-    """(rank, world_size) from torch.distributed if initialised, else from the torchrun env, else (0, 1)."""
+    """(rank, world_size) of the initialised torch.distributed process group, else (0, 1).
+
+    The torchrun environment (RANK / WORLD_SIZE) alone is NOT enough: rows are only sharded when a reduction over the
+    same group is guaranteed to follow.  Under torchrun without ``init_process_group`` every process therefore runs the
+    whole design (correct, merely redundant) instead of finalising its own shard's sums as if they were the total."""
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    return 0, 1
 
 
 def shard_range(total, rank, world_size):
@@ -29,7 +33,8 @@ def shard_range(total, rank, world_size):
 
 def allreduce_partials(partials, group=None):
     """In-place SUM all-reduce of a rank's partial-sum tensor (fp64; ~10 KB at k=20).  `partials` is a
-    torch tensor on this rank's device (cuda -> NCCL, cpu -> gloo)."""
+    torch tensor on this rank's device (cuda -> NCCL, cpu -> gloo).  Enqueued on torch's current stream: run the ctx on
+    that stream (on_torch_stream) so that the producing kernel and the finalisation are ordered around it."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
@@ -94,17 +99,67 @@ def peer_exchange(plen, device, group=None):
     return _exchanges[key]
 
 
+def use_nccl():
+    """VS_NCCL=1 selects the NCCL all-reduce (+ finalize kernel) instead of the one-launch peer-memory step."""
+    return os.environ.get("VS_NCCL", "0") == "1"
+
+
 def reduce_and_finalize(ctx, k, n, part, flags):
-    """Sum a rank's partial-sum tensor over the group and compute the indices: one NCCL all_reduce followed by
-    vs_finalize, or -- with VS_P2P=1 -- the fused peer-memory kernel (vs_allreduce_finalize_p2p) over torch symmetric
-    memory.  Measured on 8 B200 (r01): NCCL 0.850 ms per step, peer-memory kernel 0.956 ms (equal at 2 GPUs), so NCCL is
-    the default for now."""
+    """Sum a rank's partial-sum tensor over the group and compute the indices (every rank returns the same Result).
+    Default: the stand-alone peer-memory exchange kernel (vs_allreduce_finalize_p2p) over torch symmetric memory; with
+    VS_NCCL=1, or when symmetric memory is unavailable: one NCCL all_reduce followed by vs_finalize.  The collective runs
+    on torch's current stream, so the ctx is switched onto that stream for the call: the kernel that produced `part`,
+    the all-reduce and the finalisation are then ordered by the stream itself."""
     import torch
     rank, ws = world()
-    ex = None
-    if ws > 1 and os.environ.get("VS_P2P", "0") == "1":
-        ex = peer_exchange(part.numel(), part.device)
-    if ex is not None:
-        return ctx.allreduce_finalize_p2p(k, 1, n, ex.world, ex.rank, ex.peer_bufs, ex.peer_flags, ex.next_epoch(), part, flags)
-    allreduce_partials(part)
-    return ctx.finalize(k, 1, n, part, flags)
+    if ws == 1:
+        return ctx.finalize(k, 1, n, part, flags)
+    ex = None if use_nccl() else peer_exchange(part.numel(), part.device)
+    with on_torch_stream(ctx, part.device):
+        if ex is not None:
+            return ctx.allreduce_finalize_p2p(k, 1, n, ex.world, ex.rank, ex.peer_bufs, ex.peer_flags, ex.next_epoch(), part, flags)
+        allreduce_partials(part)
+        return ctx.finalize(k, 1, n, part, flags)
+
+
+class on_torch_stream(object):
+    """Run a ctx on torch's current stream for the duration of a block (vs_ctx_set_stream synchronises the stream it
+    leaves, so work enqueued before and after is ordered too); restores the ctx's own stream afterwards."""
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def __enter__(self):
+        import torch
+        self.prev = getattr(self.ctx, "_stream_ptr", None)
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        return self.ctx
+
+    def __exit__(self, *exc):
+        self.ctx.set_stream(self.prev)
+        return False
+
+
+def fused_step(ctx, k, n, perm, objective, params, discard, scale, raw, flags):
+    """The fused Saltelli step over the whole process group: this rank evaluates its contiguous shard of the n base rows
+    and every rank returns the indices of the full design.
+
+    Default (NVLink peer memory available): ONE kernel launch per rank -- vs_run_fused_p2p: generation, evaluation, Gram,
+    the all-reduce of the partial sums over peer memory and the estimators, results in mapped host memory.
+    VS_NCCL=1 (or no symmetric memory): vs_fused_partials -> one NCCL all_reduce -> vs_finalize."""
+    import torch
+    rank, ws = world()
+    if ws == 1:
+        return ctx.run_fused(k, n, perm, objective, params, discard, scale, raw, flags)
+    lo, hi = shard_range(n, rank, ws)
+    device = torch.device("cuda", ctx.device)
+    plen = partials_layout(k)["length"]
+    ex = None if use_nccl() else peer_exchange(plen, device)
+    if ex is not None and hi > lo:
+        return ctx.run_fused_p2p(k, n, perm, objective, params, ex.world, ex.rank, ex.peer_bufs, ex.peer_flags, ex.next_epoch(),
+                                 lo, hi, discard, scale, raw, flags)
+    part = torch.empty(plen, dtype=torch.float64, device=device)
+    with on_torch_stream(ctx, device):
+        ctx.fused_partials(k, n, perm, objective, params, discard, scale, raw, lo, hi, flags, out=part)
+        allreduce_partials(part)
+        return ctx.finalize(k, 1, n, part, flags)

@@ -149,8 +149,10 @@ class Sample(object):
         return out.reshape(k, n, k)
 
     def _explicit_flat(self):
-        e = self._explicit
-        return numpy.concatenate([e["M_1"], e["M_2"]] + list(e["N_j"]) + list(e["N_nj"]), axis=0)
+        if "flat" not in self._cache:                   # one concatenation, not one per window
+            e = self._explicit
+            self._cache["flat"] = numpy.concatenate([e["M_1"], e["M_2"]] + list(e["N_j"]) + list(e["N_nj"]), axis=0)
+        return self._cache["flat"]
 
     def flat(self):
         """(2n(1+k), k): rows M_1 | M_2 | N_j[0..k) | N_nj[0..k) (saltelli.py:127-160)."""
@@ -304,20 +306,27 @@ class Objective(object):
     def _evaluate_vectorized(self, max_bytes=1 << 28):
         import torch
         f, n, k = self.objective_func, self.n, self.k
-        dev = torch.device("cuda", self.sample.ctx.device)
+        ctx = self.sample.ctx
+        dev = torch.device("cuda", ctx.device)
         total = 2 * n * (1 + k)
         step = max(1, min(total, max_bytes // (8 * k)))
         block = torch.empty((step, k), dtype=torch.float64, device=dev)
         vals = None
-        for r0 in range(0, total, step):
-            r1 = min(r0 + step, total)
-            view = block[:r1 - r0]
-            self.sample.flat_rows(r0, r1, out=view)
-            v = f(view)
-            v = v.reshape(r1 - r0, -1).to(torch.float64)
-            if vals is None:
-                vals = torch.empty((total, v.shape[1]), dtype=torch.float64, device=dev)
-            vals[r0:r1] = v
+        # The export-mode kernel and the user's torch code share `block`: run the ctx on torch's current stream for the
+        # loop, so "generate window -> f(window) -> store -> generate next window" is ordered by the stream itself.
+        with dist.on_torch_stream(ctx, dev):
+            for r0 in range(0, total, step):
+                r1 = min(r0 + step, total)
+                view = block[:r1 - r0]
+                if self.sample.on_device():
+                    self.sample.flat_rows(r0, r1, out=view)
+                else:                                   # flattened-file sample: the rows live on the host
+                    view.copy_(torch.from_numpy(numpy.ascontiguousarray(self.sample.flat_rows(r0, r1), dtype=numpy.float64)))
+                v = f(view)
+                v = v.reshape(r1 - r0, -1).to(torch.float64)
+                if vals is None:
+                    vals = torch.empty((total, v.shape[1]), dtype=torch.float64, device=dev)
+                vals[r0:r1] = v
         self._vals_dev = vals
 
     def _evaluate_functor(self):
@@ -440,13 +449,4 @@ class Varsens(object):
 
     def _fused(self, o, k, n, flags):
         s, f = o.sample, o._functor
-        ctx = s.ctx
-        rank, ws = dist.world()
-        if ws == 1:
-            return ctx.run_fused(k, n, s._perm, f.objective_id, f.params(k), s.discard, s._scale, s._raw, flags)
-        import torch
-        lo, hi = dist.shard_range(n, rank, ws)
-        part = torch.empty(dist.partials_layout(k)["length"], dtype=torch.float64,
-                           device=torch.device("cuda", ctx.device))
-        ctx.fused_partials(k, n, s._perm, f.objective_id, f.params(k), s.discard, s._scale, s._raw, lo, hi, flags, out=part)
-        return dist.reduce_and_finalize(ctx, k, n, part, flags)
+        return dist.fused_step(s.ctx, k, n, s._perm, f.objective_id, f.params(k), s.discard, s._scale, s._raw, flags)
