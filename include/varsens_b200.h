@@ -110,6 +110,17 @@ int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offs
 /* The same table in any of the three term-table modes (enum vs_halton_mode); VS_HALTON_HORNER has no table: VS_ERR_UNSUPPORTED. */
 int vs_halton_terms_mode(int k, uint64_t max_index, int mode, uint32_t *ndigits, uint32_t *offsets, double *terms,
                          uint64_t capacity, uint64_t *count);
+/* Host-only self check of the fused kernels' computed-term form (terms of bases >= 37 are computed as the product of
+ * 8*digit with a double-double reciprocal instead of being looked up): 1 if it reproduces EVERY entry of the term table of
+ * `mode` bit for bit -- all digits of all positions a 32-bit index can reach, for the first k bases --, 0 if not, -1 on bad
+ * arguments.  The fused kernels refuse to run when it is 0. */
+int vs_halton_arith_check(int k, int mode);
+/* The row order ``numpy.random.seed(seed); numpy.random.shuffle(M_2)`` produces (varsens/saltelli.py:100-101, seed = 1):
+ * perm[i] = row of the unshuffled M_2 that ends up in row i.  numpy's legacy generator (MT19937, init_genrand seeding,
+ * masked-rejection rk_interval) re-implemented on uint32 with look-ahead prefetching; bit-identical to numpy for every n
+ * (tests/test_cabi_host.py).  key_out[624] / pos_out (optional) receive the generator state after the shuffle, so the caller
+ * can leave numpy's global RNG where the reference would (numpy.random.set_state(('MT19937', key, pos, 0, 0.0))). */
+int vs_reference_permutation(uint64_t n, uint32_t seed, uint32_t *perm, uint32_t *key_out, int *pos_out);
 /* Length of the partial-sum vector for k factors and l outputs: 4l + m(m+1)/2, m = (2+2k) l.
  * Layout: S_A[l], S_B[l], Q_A[l], Q_B[l] (sums / sums of squares of fM_1 - c, fM_2 - c for a
  * common shift c), then the upper triangle (row-major, t <= u) of G[t][u] = sum_i v_i[t] v_i[u]

@@ -89,6 +89,67 @@ def halton_term_table(k, max_index):
             numpy.array(offsets, dtype=numpy.uint32), numpy.array(terms, dtype=numpy.float64))
 
 
+MODES = ("divide", "reciprocal", "running_reciprocal", "horner")
+
+
+def term_table(k, max_index, mode="divide"):
+    """The term table in one of the alternative fp64 arithmetics the library can be switched to (enum vs_halton_mode,
+    include/varsens_b200.h) -- candidates for what an actual ghalton build does, should it ever disagree with the restatement
+    above (tests/golden/make_ghalton_golden.py turns a real install into goldens):
+      divide              term = digit / b^(j+1)                   (the restatement above)
+      reciprocal          term = digit * (1.0 / b^(j+1))
+      running_reciprocal  term = digit * f_j, f_0 = 1.0 / b, f_{j+1} = f_j * (1.0 / b)
+    Returns dict(bases, ndigits, offsets, terms)."""
+    if mode not in MODES[:3]:
+        raise ValueError("mode %r has no term table" % (mode,))
+    bases, ndigits, offsets, _ = halton_term_table(k, max_index)
+    terms = []
+    for b, nd in zip(bases.tolist(), ndigits.tolist()):
+        bp = float(b)
+        ib = 1.0 / float(b)
+        f = ib
+        for _ in range(nd):
+            for digit in range(b):
+                if mode == "divide":
+                    terms.append(float(digit) / bp)
+                elif mode == "reciprocal":
+                    terms.append(float(digit) * (1.0 / bp))
+                else:
+                    terms.append(float(digit) * f)
+            bp *= b
+            f = f * ib
+    return dict(bases=bases, ndigits=ndigits, offsets=offsets, terms=numpy.array(terms, dtype=numpy.float64))
+
+
+def halton_points_mode(k, first_index, count, mode="divide"):
+    """(count, k) points in any of MODES.  The three term-table modes sum table entries least significant digit first;
+    ``horner`` evaluates x = (x + digit_j) / b from the most significant digit down (one division per digit)."""
+    first_index, count = int(first_index), int(count)
+    out = numpy.zeros((count, int(k)), dtype=numpy.float64)
+    if mode == "horner":
+        for d, b in enumerate(first_primes(k)):
+            for r in range(count):
+                m, digits = first_index + r, []
+                while m > 0:
+                    digits.append(m % b)
+                    m //= b
+                x = 0.0
+                for dg in reversed(digits):
+                    x = (x + float(dg)) / float(b)
+                out[r, d] = x
+        return out
+    t = term_table(k, first_index + count - 1, mode)
+    for d, b in enumerate(t["bases"].tolist()):
+        rows = t["terms"][t["offsets"][d]:].reshape(-1)[: t["ndigits"][d] * b].reshape(t["ndigits"][d], b)
+        m = numpy.arange(first_index, first_index + count, dtype=numpy.uint64)
+        x = numpy.zeros(count)
+        for j in range(int(t["ndigits"][d])):
+            x = x + rows[j][(m % numpy.uint64(b)).astype(numpy.int64)]
+            m //= numpy.uint64(b)
+        out[:, d] = x
+    return out
+
+
 class Halton(object):
     """Stateful stand-in with ghalton's interface: ``Halton(k).get(n)`` -> list of lists."""
 

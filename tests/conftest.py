@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    config.addinivalue_line("markers", "slow_cpu: CPU test that takes a few seconds (full-size permutation)")
 
 
 @pytest.fixture(scope="session")

@@ -213,6 +213,112 @@ def test_reference_permutation_cache_keeps_rng_side_effect():
     assert len(vsalt._perm_cache) <= 4
 
 
+def test_c_permutation_equals_numpy_legacy_shuffle(cabi):
+    """vs_reference_permutation (MT19937 + masked-rejection rk_interval on uint32, look-ahead prefetch) against the
+    reference's own call, numpy.random.seed(1); numpy.random.shuffle (saltelli.py:100-101): the permutation, shuffling a
+    2-D matrix (what the reference shuffles), and the generator state it leaves behind."""
+    for n in list(range(0, 70)) + [127, 128, 129, 255, 256, 257, 1000, 4095, 4096, 4097, 65535, 65536, 65537, 1 << 20, (1 << 20) + 3]:
+        perm, state = cabi.reference_permutation(n, 1)
+        idx = numpy.arange(n)
+        numpy.random.seed(1)
+        numpy.random.shuffle(idx)
+        want_state = numpy.random.get_state()
+        assert perm.dtype == numpy.uint32 and (perm == idx).all(), n
+        assert state[2] == want_state[2] and (state[1] == want_state[1]).all(), n      # same position, same key
+    for seed in (0, 7, 2 ** 32 - 1):
+        perm, state = cabi.reference_permutation(5000, seed)
+        m = numpy.arange(5000 * 3).reshape(5000, 3)
+        numpy.random.seed(seed)
+        numpy.random.shuffle(m)                                                        # 2-D: rows are shuffled, same draws
+        assert (m[:, 0] // 3 == perm).all()
+        numpy.random.set_state(state)
+        a = numpy.random.random_sample(4)
+        b = numpy.random.random_sample(4)
+        numpy.random.seed(seed)
+        numpy.random.shuffle(numpy.arange(5000))
+        assert (numpy.random.random_sample(4) == a).all() and (numpy.random.random_sample(4) == b).all()
+
+
+@pytest.mark.slow_cpu
+def test_c_permutation_full_size(cabi):
+    """n = 2^24 (BASELINE config 3): equal to numpy's legacy shuffle, first values as frozen in SURVEY.md App. D."""
+    perm, state = cabi.reference_permutation(1 << 24, 1)
+    assert perm[:5].tolist() == [1374744, 606845, 6252930, 11816538, 1572451]
+    assert (perm == numpy.random.RandomState(1).permutation(1 << 24)).all()
+
+
+def test_computed_halton_terms_equal_the_table(cabi):
+    """fused_impl.cuh digit_step_arith: the double-double-reciprocal form of digit / b^(j+1) must reproduce the term table bit
+    for bit -- every digit of every position a 32-bit index reaches -- in each term-table mode (host self check of the
+    library, exhaustive) and here once more in Python for the default mode with exact rational arithmetic as the referee."""
+    from fractions import Fraction
+    lib = cabi.lib()
+    for mode in (cabi.HALTON_DIVIDE, cabi.HALTON_RECIPROCAL, cabi.HALTON_RUNNING_RECIPROCAL):
+        assert lib.vs_halton_arith_check(64, mode) == 1
+    assert lib.vs_halton_arith_check(20, 99) == -1
+    # independent referee: the table's DIVIDE terms are the correctly rounded quotients digit / b^(j+1)
+    bases, nd, off, terms = cabi.halton_terms(20, 2 ** 32 - 1)
+    checked = 0
+    for d in (1, 5, 11, 19):
+        b = int(bases[d])
+        for j in range(int(nd[d])):
+            for digit in range(b):
+                t = float(terms[off[d] + j * b + digit])
+                assert t == digit / float(b ** (j + 1))
+                exact = Fraction(digit, b ** (j + 1))
+                ulp = numpy.spacing(t) if t else 0.0
+                assert abs(Fraction(t) - exact) <= Fraction(ulp) / 2               # correctly rounded
+                checked += 1
+    assert checked > 500
+
+
+def test_halton_term_table_modes(cabi):
+    """The three term-table arithmetics (enum vs_halton_mode) against the oracle's restatement of each."""
+    from oracle import halton as oh
+    for mode, name in ((cabi.HALTON_DIVIDE, "divide"), (cabi.HALTON_RECIPROCAL, "reciprocal"),
+                       (cabi.HALTON_RUNNING_RECIPROCAL, "running_reciprocal")):
+        bases, nd, off, terms = cabi.halton_terms(12, 10 ** 7, mode)
+        want = oh.term_table(12, 10 ** 7, mode=name)
+        assert (terms == want["terms"]).all() and (off == want["offsets"]).all() and (nd == want["ndigits"]).all()
+    d, r = cabi.halton_terms(12, 10 ** 7, cabi.HALTON_DIVIDE)[3], cabi.halton_terms(12, 10 ** 7, cabi.HALTON_RECIPROCAL)[3]
+    assert (d != r).any() and numpy.abs(d - r).max() < 2.3e-16                     # the modes really differ, by an ulp
+    with pytest.raises(cabi.VarsensError):
+        cabi.halton_terms(12, 100, cabi.HALTON_HORNER)
+
+
+def test_quantlib_initializer_reader(tmp_path):
+    """varsens_b200.sobol.quantlib_direction_numbers: parse QuantLib-style initialiser arrays (C source with a pointer table,
+    C source without one, plain text) and run QuantLib's recurrence.  Pinned by writing scipy's Joe-Kuo initialisers in those
+    formats: the direction integers must equal the Joe-Kuo table the Sobol kernel is already pinned on."""
+    import scipy
+    from varsens_b200 import sobol as vsobol, _cabi
+    z = numpy.load(os.path.join(os.path.dirname(scipy.__file__), "stats", "_sobol_direction_numbers.npz"))
+    k = 40
+    want = vsobol.joe_kuo_direction_numbers(k)
+    inits = []
+    for d in range(1, k):
+        s_ = int(z["poly"][d]).bit_length() - 1
+        inits.append([int(v) for v in z["vinit"][d][:s_]])
+    names = ["dim%02dLevitanLemieuxinitializers" % (d + 2) for d in range(len(inits))]
+    src = "// excerpt in the layout of ql/math/randomnumbers/sobolrsg.cpp\nnamespace {\n"
+    for nm, m in zip(names, inits):
+        src += "    static const unsigned long %s[] = {\n        %s, 0UL };\n" % (nm, ", ".join("%dUL" % v for v in m))
+    decoy = "    static const unsigned long dim02Kuoinitializers[] = { 1UL, 0UL };\n"
+    table = "    static const unsigned long * const LevitanLemieuxinitializers[%d] = {\n        %s\n    };\n}\n" % (
+        len(names), ",\n        ".join(names))
+    path = tmp_path / "sobolrsg.cpp"
+    path.write_text(src + decoy + table)
+    assert (vsobol.quantlib_direction_numbers(k, str(path)) == want).all()
+    assert (vsobol.quantlib_direction_numbers(k, src + decoy, kind="LevitanLemieux") == want).all()       # no pointer table
+    txt = "# dimension 2 onwards\n" + "\n".join(" ".join(str(v) for v in m) for m in inits)
+    assert (vsobol.quantlib_direction_numbers(k, txt) == want).all()
+    assert (vsobol.quantlib_direction_numbers(2, "1\n") == want[:2]).all()
+    with pytest.raises(_cabi.VarsensError):
+        vsobol.quantlib_direction_numbers(k, "1\n1 3\n")                                                 # too few dimensions
+    with pytest.raises(_cabi.VarsensError):
+        vsobol.quantlib_direction_numbers(3, "1\n2 3\n")                                                 # even initialiser
+
+
 def test_header_enums_match_python_binding():
     """The ctypes binding hard-codes the header's enum values: parse include/varsens_b200.h and compare."""
     from varsens_b200 import _cabi

@@ -3,6 +3,8 @@ reference's own known-answer tests.  CPU only."""
 import itertools
 import math
 
+import os
+
 import numpy
 import pytest
 
@@ -252,3 +254,31 @@ def test_halton_sequence_definition_against_scipy():
         return
     theirs_far = numpy.stack([van_der_corput(16, int(b), start_index=33554000) for b in halton.first_primes(k)], axis=1)
     assert (numpy.abs(theirs_far - far) / numpy.spacing(far)).max() <= 2.0
+
+
+GHALTON_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ghalton_golden.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GHALTON_GOLDEN), reason="no ghalton goldens: run tests/golden/make_ghalton_golden.py where "
+                    "ghalton installs (parity with the third-party generator stays unpinned until then)")
+def test_ghalton_golden():
+    """Activates once tests/golden/ghalton_golden.npz (outputs of a real ghalton install) is committed: the default Halton
+    arithmetic must be bit-identical to it; otherwise the message names the selectable mode that is."""
+    from oracle import halton as oh
+    g = numpy.load(GHALTON_GOLDEN)
+    verdict = {}
+    for mode in oh.MODES:
+        ok = True
+        for key in g.files:
+            if key == "ghalton_version":
+                continue
+            want = g[key]
+            if key == "k4_after_2p25":
+                got = oh.halton_points_mode(4, (1 << 25) + 1, want.shape[0], mode)
+            else:
+                k, n, d = (int(x[1:]) for x in key.split("_"))
+                got = oh.halton_points_mode(k, 20 * k + d + 1, 2 * n, mode)
+            ok = ok and got.shape == want.shape and bool((got == want).all())
+        verdict[mode] = ok
+    assert verdict["divide"], "ghalton %s is NOT reproduced by the default arithmetic; matching modes: %s -- set VS_HALTON_MODE" % (
+        g["ghalton_version"], [m for m, v in verdict.items() if v])

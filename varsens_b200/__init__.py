@@ -8,7 +8,7 @@ from .saltelli import Varsens, Sample, Objective
 from .scale import *          # noqa: F401,F403  (the reference star-exports linear/power/percentage/magnitude)
 from . import scale
 from .functors import GFunction, Ishigami, RK4Chain, vectorized
-from .sobol import sobol_raw, joe_kuo_direction_numbers
+from .sobol import sobol_raw, joe_kuo_direction_numbers, quantlib_direction_numbers, read_sobol_initializers
 from ._cabi import Context, VarsensError
 
 __all__ = ['scale', 'Varsens', 'Sample', 'Objective']

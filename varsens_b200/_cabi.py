@@ -25,6 +25,7 @@ SYMBOLS = (
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
     "vs_finalize_device", "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
     "vs_ctx_reload_env", "vs_ctx_set_halton_mode", "vs_halton_terms_mode", "vs_run_fused_p2p", "vs_last_tail_ns",
+    "vs_halton_arith_check", "vs_reference_permutation",
 )
 HALTON_DIVIDE, HALTON_RECIPROCAL, HALTON_RUNNING_RECIPROCAL, HALTON_HORNER = 0, 1, 2, 3
 ERR_TIMEOUT = 6
@@ -90,6 +91,8 @@ def lib():
         L.vs_ctx_set_halton_mode.argtypes = [vp, i32]
         L.vs_halton_terms_mode.argtypes = [i32, u64, i32, vp, vp, vp, u64, P(u64)]
         L.vs_last_tail_ns.argtypes = [vp, i32, vp]
+        L.vs_halton_arith_check.argtypes = [i32, i32]
+        L.vs_reference_permutation.argtypes = [u64, ctypes.c_uint32, vp, vp, P(i32)]
         L.vs_measure_fp64_peak.argtypes = [vp, P(ctypes.c_double)]
         L.vs_last_kernel_ms.argtypes = [vp, P(ctypes.c_float)]
         for name in SYMBOLS:
@@ -409,6 +412,18 @@ def _run_fused_p2p(self, k, n, perm, objective, params, world_size, rank, peer_b
 
 
 Context.run_fused_p2p = _run_fused_p2p
+
+
+def reference_permutation(n, seed=1):
+    """(perm uint32[n], numpy legacy RNG state after the shuffle) of ``numpy.random.seed(seed); numpy.random.shuffle(rows)``
+    (varsens/saltelli.py:100-101), computed by the library's own MT19937 (host code, no GPU needed)."""
+    n = int(n)
+    perm = numpy.empty(n, dtype=numpy.uint32)
+    key = numpy.empty(624, dtype=numpy.uint32)
+    pos = ctypes.c_int()
+    check(lib().vs_reference_permutation(n, int(seed), perm.ctypes.data_as(ctypes.c_void_p), key.ctypes.data_as(ctypes.c_void_p),
+                                         ctypes.byref(pos)))
+    return perm, ("MT19937", key, int(pos.value), 0, 0.0)
 
 
 def halton_terms(k, max_index, mode=HALTON_DIVIDE):

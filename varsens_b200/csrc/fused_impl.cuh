@@ -38,8 +38,17 @@ __host__ __device__ constexpr int gram_tile_for(int M) {
     return T;
 }
 
+// B-point terms of the large bases are computed instead of looked up (see digit_step_arith): dimensions >= AR_D0.
+#ifndef VS_ARITH_D0
+#define VS_ARITH_D0 11         // prime_at(11) = 37: rows of >= 37 doubles span > 32 banks, random lookups cost 3-5 wavefronts
+#endif
+constexpr int AR_D0 = VS_ARITH_D0;
+constexpr int AR_J = 7;        // digit positions of a 32-bit index in base >= 37
+
 template <int K>
 struct FusedConst {            // kernel parameter -> constant bank; indexed with compile-time subscripts
+    static constexpr int AR_N = K > AR_D0 ? K - AR_D0 : 1;
+    double arh[AR_N][AR_J], arl[AR_N][AR_J];   // term of digit at position j of dimension AR_D0 + u = fma(dd, arh, dd * arl), dd = 8 * digit
     double lb[K], wr[K];
     uint32_t toff[K];          // offset of dimension d's terms inside the shared copy of the table
     uint32_t nd[K];            // digits to sum for the largest index of the run
@@ -176,6 +185,13 @@ __host__ __device__ constexpr int ndmax32(uint32_t b) {
     for (uint64_t m = 0xFFFFFFFFull; m > 0; m /= b) ++c;
     return c;
 }
+// digits of the largest IB-bit index in base b: the digit positions a run whose indices are all < 2^IB has to visit
+template <int IB>
+__host__ __device__ constexpr int nd_ib(uint32_t b) {
+    int c = 0;
+    for (uint64_t m = (IB >= 32 ? 0xFFFFFFFFull : ((1ull << IB) - 1ull)); m > 0; m /= b) ++c;
+    return c;
+}
 __host__ __device__ constexpr uint32_t foff(int d) {          // dimension 0 (base 2) needs no table
     uint32_t s = 0;
     for (int e = 1; e < d; ++e) s += prime_at(e) * (uint32_t)ndmax32(prime_at(e));
@@ -222,15 +238,44 @@ __device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *_
     x = __dadd_rn(x, *reinterpret_cast<const double *>(row + off8));
 }
 
+// The same step with the term COMPUTED instead of looked up (B-points of bases >= 37, whose table rows span more than the
+// 32 banks: a random 8-byte lookup costs 3-5 shared-memory wavefronts, and generation is bound by that SM-wide pipe while
+// the FP64 pipe idles).  With dd = 8 * digit exact in fp64 (magic-number conversion, one DADD) the term digit / b^(j+1) is
+//   fma(dd, rh, dd * rl),   rh = RN(1 / b^(j+1)) / 8,  rl = RN(1 / b^(j+1) - RN(1 / b^(j+1))) / 8
+// i.e. the product of dd with a double-double reciprocal, rounded once.  Its error before the final rounding is < 2^-104
+// relative, while digit / b^(j+1) (odd denominator) stays >= 2^-85 relative away from every rounding boundary, so the
+// result IS the correctly rounded quotient; on top of the argument the host compares all digits of all positions against
+// the term table when the constants are built (host.cu: build_arith) and refuses the fused kernel on any mismatch.
+// The other term-table modes use rl = 0 and rh = their factor: the same instruction sequence gives RN(digit * factor).
+template <uint32_t B, bool FAST>
+__device__ __forceinline__ void digit_step_arith(uint32_t &m, double &x, double rh, double rl) {
+    uint32_t off8;
+    if constexpr (FAST) {
+        constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
+        const uint64_t w = (uint64_t)m * C;
+        off8 = __umulhi((uint32_t)w, 8u * B);
+        m = (uint32_t)(w >> 32);
+    } else {
+        const uint32_t q = m / B;
+        off8 = (m - q * B) * 8u;
+        m = q;
+    }
+    const double dd = __dadd_rn(__hiloint2double(0x43300000, (int)off8), -4503599627370496.0);
+    x = __dadd_rn(x, __fma_rn(dd, rh, __dmul_rn(dd, rl)));
+}
+
 // Halton digit sums of the two indices ia (A_i) and ib (B_i) for one GROUP of HG dimensions: 2*HG independent
 // (index, sum) chains advance together, least-significant digit first; the group stops after the largest digit
 // count it needs for this run (warp-uniform).  Group 0 also emits dimension 0: base 2, where every partial sum
 // is exact and the in-order digit sum is a bit reversal.
-constexpr int HG = 4;
+#ifndef VS_HG
+#define VS_HG 4
+#endif
+constexpr int HG = VS_HG;
 template <int K>
 __host__ __device__ constexpr int halton_groups() { return K > 1 ? (K - 1 + HG - 1) / HG : 1; }
 
-template <int K, int SCALE, int G, class Emit>
+template <int K, int SCALE, int G, int IB, class Emit>
 __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const double *__restrict__ terms, uint32_t ia, uint32_t ib,
                                              Emit &&emit) {
     if constexpr (G == 0)
@@ -239,7 +284,7 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
     constexpr int D0 = 1 + G * HG;
     if constexpr (D0 < K) {
         constexpr int N = (K - D0) < HG ? (K - D0) : HG;
-        constexpr int JMAX = ndmax32(prime_at(D0));         // the smallest base of the group has the most digits
+        constexpr int JMAX = nd_ib<IB>(prime_at(D0));       // the smallest base of the group has the most digits
         uint32_t ma[N], mb[N];
         double xa[N], xb[N];
         int ndmax = 0;
@@ -252,11 +297,12 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
             ndmax = ndmax > (int)fc.nd[D0 + u] ? ndmax : (int)fc.nd[D0 + u];
         }
         const char *tb = reinterpret_cast<const char *>(terms);
-        const bool small = fc.small_index != 0;             // every index of the run < 2^29: FAST from digit 1 on
-        // All JMAX digit positions are executed unconditionally: one straight-line block per group, so the
-        // scheduler can run the index chains ahead and keep many table loads in flight (with a branch per digit
-        // the loads of digit j+1 could not be hoisted over the additions of digit j and every digit paid a full,
-        // queue-inflated LDS latency).  Positions beyond the run's digit count see m == 0 and add +0.0 (exact).
+        const bool small = IB <= 29 || fc.small_index != 0; // every index of the run < 2^29: FAST from digit 1 on
+        // All digit positions an IB-bit index can have are executed unconditionally: one straight-line block per group, so
+        // the scheduler can run the index chains ahead and keep many table loads in flight (with a branch per digit the
+        // loads of digit j+1 could not be hoisted over the additions of digit j and every digit paid a full, queue-inflated
+        // LDS latency).  Positions beyond a run's digit count see m == 0 and add +0.0 (exact).  IB is a template parameter
+        // (26 or 32): BASELINE's configs all stay below 2^26 and visit 132 instead of 159 positions per point at k = 20.
         (void)ndmax;
         static_for<JMAX>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value;
@@ -264,20 +310,26 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
                 static_for<N>([&](auto Uc) {
                     constexpr int U = decltype(Uc)::value;
                     constexpr uint32_t B = prime_at(D0 + U);
-                    if constexpr (J < ndmax32(B)) {
+                    if constexpr (J < nd_ib<IB>(B)) {
                         const char *row = tb + (size_t)(foff(D0 + U) + J * B) * 8;
+                        constexpr bool AR = (D0 + U) >= AR_D0;               // B-point term computed, not looked up
+                        constexpr int AU = AR ? (D0 + U - AR_D0) : 0, AJ = J < AR_J ? J : AR_J - 1;
                         if constexpr (J == 0) {
                             digit_step<B, false>(ma[U], xa[U], row);
-                            digit_step<B, false>(mb[U], xb[U], row);
-                        } else if constexpr (J >= jfast(B)) {
+                            if constexpr (AR) digit_step_arith<B, false>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, false>(mb[U], xb[U], row);
+                        } else if constexpr (J >= jfast(B) || IB <= 29) {
                             digit_step<B, true>(ma[U], xa[U], row);
-                            digit_step<B, true>(mb[U], xb[U], row);
+                            if constexpr (AR) digit_step_arith<B, true>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, true>(mb[U], xb[U], row);
                         } else if (small) {
                             digit_step<B, true>(ma[U], xa[U], row);
-                            digit_step<B, true>(mb[U], xb[U], row);
+                            if constexpr (AR) digit_step_arith<B, true>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, true>(mb[U], xb[U], row);
                         } else {
                             digit_step<B, false>(ma[U], xa[U], row);
-                            digit_step<B, false>(mb[U], xb[U], row);
+                            if constexpr (AR) digit_step_arith<B, false>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, false>(mb[U], xb[U], row);
                         }
                     }
                 });
@@ -288,7 +340,7 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
     }
 }
 
-template <int K, int SCALE, class Emit>
+template <int K, int SCALE, int IB, class Emit>
 __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
                                          uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
     uint64_t r = bt * 32 + lane;
@@ -301,18 +353,18 @@ __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedC
         for (int d = 0; d < K; ++d) emit(d, scale_coord<K, SCALE>(fc, d, ra[d]), scale_coord<K, SCALE>(fc, d, rb[d]));
     } else {
         const uint32_t ia = (uint32_t)(src.start + i), ib = (uint32_t)(src.start + src.n + pi);
-        static_for<halton_groups<K>()>([&](auto Gc) { halton_group<K, SCALE, decltype(Gc)::value>(fc, terms, ia, ib, emit); });
+        static_for<halton_groups<K>()>([&](auto Gc) { halton_group<K, SCALE, decltype(Gc)::value, IB>(fc, terms, ia, ib, emit); });
     }
     return valid;
 }
 
 // One warp-uniform branch on the scale kind for the whole row (not one per coordinate).
-template <int K, class Emit>
+template <int K, int IB = 32, class Emit>
 __device__ __forceinline__ bool gen_rows(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
                                          uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
-    if (fc.scale_kind == VS_SCALE_IDENTITY) return gen_rows_impl<K, VS_SCALE_IDENTITY>(src, fc, terms, i_begin, rows, bt, lane, emit);
-    if (fc.scale_kind == VS_SCALE_LINEAR) return gen_rows_impl<K, VS_SCALE_LINEAR>(src, fc, terms, i_begin, rows, bt, lane, emit);
-    return gen_rows_impl<K, VS_SCALE_POWER>(src, fc, terms, i_begin, rows, bt, lane, emit);
+    if (fc.scale_kind == VS_SCALE_IDENTITY) return gen_rows_impl<K, VS_SCALE_IDENTITY, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
+    if (fc.scale_kind == VS_SCALE_LINEAR) return gen_rows_impl<K, VS_SCALE_LINEAR, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
+    return gen_rows_impl<K, VS_SCALE_POWER, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
 }
 
 // Generic evaluation of EG design points of one base row for a product-form functor (see eval_rows).
@@ -709,12 +761,11 @@ __device__ __forceinline__ double packed_entry(const double *__restrict__ D, int
     }
 }
 
-constexpr int TAIL_PARTS = 8;
 template <int K, int NB, int HB, bool PM>
 __host__ __device__ constexpr size_t wsd_tail_smem_doubles() {
     constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
-    return (size_t)TAIL_PARTS * LROW + LROW + 2 * (size_t)(plen + 4) + rlen + 8;
+    return (size_t)128 + LROW + 2 * (size_t)(plen + 4) + rlen + 8;
 }
 
 // Runs in the last CTA to finish (all threads).  smem: dynamic shared memory of the kernel, free for reuse.
@@ -723,43 +774,58 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int NTL = wsd_ntl<NB, HB, PM>();
     constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
-    double *ps = smem;                                     // [TAIL_PARTS][LROW]
-    double *D = ps + (size_t)TAIL_PARTS * LROW;            // [LROW]
+    double *ps = smem;                                     // [128] scratch
+    double *D = ps + 128;                                  // [LROW]
     double *Pk = D + LROW;                                 // [plen] packed partial sums of this rank
     double *Pr = Pk + plen + 4;                            // [plen] reduced over ranks (mode 2)
     double *R = Pr + plen + 4;                             // [rlen] results
     const int tid = threadIdx.x, nthr = blockDim.x, nb = gridDim.x;
     const unsigned long long t0 = globaltimer_ns();
-    // 1. CTA rows -> D, fixed order: TAIL_PARTS contiguous ranges of CTAs summed in CTA order, then the parts in part order
+    // 1. CTA rows -> D in CTA order.  One double2 column (= one lane's C fragment of one tile) per thread, 32 independent
+    //    loads in flight per thread: the 0.9 MB of CTA rows come through ONE SM, so memory-level parallelism is what counts
+    //    (8 ranges x 4 loads in flight took 18 us here; this form 3-4 us).  The four shifted sums are done by warp 0,
+    //    lane l adding CTAs l, l+32, ... in order, then the lanes in lane order.
     {
         constexpr int L2 = LROW / 2;
-        const int per = (nb + TAIL_PARTS - 1) / TAIL_PARTS;
-        for (int task = tid; task < TAIL_PARTS * L2; task += nthr) {
-            const int part = task / L2, c2 = task - part * L2;
-            int b = part * per;
-            const int b1 = (b + per < nb) ? b + per : nb;
-            const double2 *src = reinterpret_cast<const double2 *>(tail.blockpart) + c2;
+        const double2 *base = reinterpret_cast<const double2 *>(tail.blockpart);
+        for (int c2 = tid; c2 < NTL * 32; c2 += nthr) {
+            const double2 *src = base + c2;
             double2 acc = make_double2(0.0, 0.0);
-            for (; b + 4 <= b1; b += 4) {
-                double2 v0 = __ldcg(src + (size_t)(b + 0) * L2), v1 = __ldcg(src + (size_t)(b + 1) * L2);
-                double2 v2 = __ldcg(src + (size_t)(b + 2) * L2), v3 = __ldcg(src + (size_t)(b + 3) * L2);
-                acc.x += v0.x; acc.y += v0.y;
-                acc.x += v1.x; acc.y += v1.y;
-                acc.x += v2.x; acc.y += v2.y;
-                acc.x += v3.x; acc.y += v3.y;
+            int b = 0;
+            for (; b + 32 <= nb; b += 32) {
+                double2 v[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
+#pragma unroll
+                for (int u = 0; u < 32; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
             }
-            for (; b < b1; ++b) {
-                double2 v = __ldcg(src + (size_t)b * L2);
+            for (; b + 4 <= nb; b += 4) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+            }
+            for (; b < nb; ++b) {
+                const double2 v = __ldcg(src + (size_t)b * L2);
                 acc.x += v.x; acc.y += v.y;
             }
-            reinterpret_cast<double2 *>(ps + (size_t)part * LROW)[c2] = acc;
+            reinterpret_cast<double2 *>(D)[c2] = acc;
         }
-        __syncthreads();
-        for (int e = tid; e < LROW; e += nthr) {
-            double v = 0.0;
-#pragma unroll
-            for (int part = 0; part < TAIL_PARTS; ++part) v += ps[(size_t)part * LROW + e];
-            D[e] = v;
+        if (tid < 32) {
+            double2 s01 = make_double2(0.0, 0.0), s23 = make_double2(0.0, 0.0);
+            for (int b = tid; b < nb; b += 32) {
+                const double2 v0 = __ldcg(base + (size_t)b * L2 + NTL * 32), v1 = __ldcg(base + (size_t)b * L2 + NTL * 32 + 1);
+                s01.x += v0.x; s01.y += v0.y; s23.x += v1.x; s23.y += v1.y;
+            }
+            double *lane4 = ps + tid * 4;                   // ps: scratch
+            lane4[0] = s01.x; lane4[1] = s01.y; lane4[2] = s23.x; lane4[3] = s23.y;
+            __syncwarp();
+            if (tid < 4) {
+                double v = 0.0;
+                for (int l = 0; l < 32; ++l) v += ps[l * 4 + tid];
+                D[NTL * 64 + tid] = v;
+            }
         }
         __syncthreads();
     }
@@ -828,29 +894,27 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     __threadfence_system();
 }
 
-// Coordinate d of the Halton point m from the fixed-layout shared table (run-time d; used once per CTA for the shift).
-__device__ __forceinline__ uint32_t prime_rt(int d) {
-    uint32_t p = 2;
-#pragma unroll 1
-    for (int e = 0; e < d; ++e) {
-        for (++p;; ++p) {
-            bool pr = true;
-            for (uint32_t q = 2; q * q <= p; ++q)
-                if (p % q == 0) { pr = false; break; }
-            if (pr) break;
-        }
+// Coordinate d (run-time: lane = coordinate, no divergence) of the Halton point m from the fixed-layout shared table; used
+// once per CTA, for the common shift.  Bases and row offsets come from a compile-time table.
+template <int K>
+struct FixedTab {
+    uint32_t base[K], off[K];
+};
+template <int K>
+__host__ __device__ constexpr FixedTab<K> make_fixed_tab() {
+    FixedTab<K> t{};
+    for (int d = 0; d < K; ++d) {
+        t.base[d] = prime_at(d);
+        t.off[d] = d == 0 ? 0u : foff(d);
     }
-    return p;
+    return t;
 }
+template <int K>
 __device__ __forceinline__ double halton_coord_fixed(const double *__restrict__ terms, int d, uint32_t m) {
+    constexpr FixedTab<K> tab = make_fixed_tab<K>();
     if (d == 0) return (double)__brev(m) * 2.3283064365386962890625e-10;
-    uint32_t off = 0, b = 2;
-#pragma unroll 1
-    for (int e = 1; e <= d; ++e) {
-        b = prime_rt(e);
-        if (e < d) off += b * (uint32_t)ndmax32(b);
-    }
-    const double *row = terms + off;
+    const uint32_t b = tab.base[d];
+    const double *row = terms + tab.off[d];
     double x = 0.0;
     while (m != 0u) {
         const uint32_t q = m / b;
@@ -861,7 +925,7 @@ __device__ __forceinline__ double halton_coord_fixed(const double *__restrict__ 
     return x;
 }
 
-template <int K, class F, bool SEPARABLE, int EPS, int NBUF>
+template <int K, class F, bool SEPARABLE, int EPS, int NBUF, int IB>
 __global__ void __launch_bounds__((EPS + 1) * WS_S * 32, 1)
 fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_end, FusedTail tail) {
     constexpr int WS_E = EPS * WS_S;
@@ -892,9 +956,9 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     }
     __syncthreads();
     // common shift of the variance sums, f(M_1[0]): every CTA (and every rank) derives the same bits from base row 0
-    if (threadIdx.x < K) {
+    if (threadIdx.x < K) {                                // lane = coordinate: the table reads of the K chains overlap
         const int d = threadIdx.x;
-        double p = src.raw ? src.raw[d] : halton_coord_fixed(terms, d, (uint32_t)src.start);
+        double p = src.raw ? src.raw[d] : halton_coord_fixed<K>(terms, d, (uint32_t)src.start);
         if (fc.scale_kind == VS_SCALE_LINEAR) p = __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);
         else if (fc.scale_kind == VS_SCALE_POWER) p = __dmul_rn(fc.lb[d], pow(fc.wr[d], p));
         xs_sh[d] = p;
@@ -964,7 +1028,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 #pragma unroll
                 for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
             } else {
-                valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+                valid = gen_rows<K, IB>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
                     a[d] = xa;
                     b[d] = xb;
                 });
@@ -1161,11 +1225,20 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             size_t smem = smem_run > smem_red ? smem_run : smem_red;
             if (smem_tail > smem) smem = smem_tail;
             VS_REQUIRE(smem <= c->smem_optin, VS_ERR_UNSUPPORTED, "fused kernel needs %zu bytes of shared memory", smem);
-            auto kern = variant == 6 ? fused_wsd_kernel<K, F, SEPARABLE, 3, 1> : fused_wsd_kernel<K, F, SEPARABLE, 2, 1>;
-            static size_t smem_set[64][2] = {};                  // per instantiation and device: set the attribute once per size
-            if (c->device >= 64 || smem_set[c->device][variant == 6] < smem) {
+            // index-bit class: runs whose Halton indices all stay below 2^26 (every BASELINE config) visit fewer digit positions
+            const bool ib26 = !src.raw && (src.start + 2 * src.n - 1) < (1ull << 26) && c->opt.index_bits != 32;
+#ifdef VS_EXP_MINIMAL                                            // experiment builds: one instantiation only
+            VS_REQUIRE(ib26 && variant == 5, VS_ERR_UNSUPPORTED, "experiment build: variant 5, indices < 2^26 only");
+            auto kern = fused_wsd_kernel<K, F, SEPARABLE, 2, 1, 26>;
+#else
+            auto kern = variant == 6 ? (ib26 ? fused_wsd_kernel<K, F, SEPARABLE, 3, 1, 26> : fused_wsd_kernel<K, F, SEPARABLE, 3, 1, 32>)
+                                     : (ib26 ? fused_wsd_kernel<K, F, SEPARABLE, 2, 1, 26> : fused_wsd_kernel<K, F, SEPARABLE, 2, 1, 32>);
+#endif
+            const int ki = (variant == 6 ? 2 : 0) + (ib26 ? 1 : 0);
+            static size_t smem_set[64][4] = {};                  // per instantiation and device: set the attribute once per size
+            if (c->device >= 64 || smem_set[c->device][ki] < smem) {
                 VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                if (c->device < 64) smem_set[c->device][variant == 6] = smem;
+                if (c->device < 64) smem_set[c->device][ki] = smem;
             }
             time_begin(c);
             kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, tail);
@@ -1235,6 +1308,8 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
     fc.small_index = 0;
     fc.trace = nullptr;
     fc.alternate = c->opt.alternate;
+    for (int u = 0; u < FusedConst<K>::AR_N; ++u)
+        for (int j = 0; j < AR_J; ++j) { fc.arh[u][j] = 0.0; fc.arl[u][j] = 0.0; }
     if (!c->opt.trace.empty()) {
         VS_TRY(ensure(c, c->dir_buf, 16 * 64 * 4 * sizeof(long long)));
         VS_CUDA(cudaMemsetAsync(c->dir_buf.p, 0, 16 * 64 * 4 * sizeof(long long), c->stream));
@@ -1252,6 +1327,15 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
         }
         // the cached table may have more digits than this run needs: its layout is what matters
         fc.small_index = (src.start + 2 * src.n - 1) < (1ull << 29) ? 1 : 0;
+        if (K > AR_D0) {
+            VS_REQUIRE(c->halton.arith_ok, VS_ERR_UNSUPPORTED, "computed Halton terms do not reproduce the term table in mode %d",
+                       c->halton.mode);
+            for (int u = 0; u < K - AR_D0; ++u)
+                for (int j = 0; j < AR_J; ++j) {
+                    fc.arh[u][j] = c->halton.arh[(size_t)(AR_D0 + u) * AR_J + j];
+                    fc.arl[u][j] = c->halton.arl[(size_t)(AR_D0 + u) * AR_J + j];
+                }
+        }
         VS_REQUIRE(off == src.h.total_terms, VS_ERR_ARG, "Halton table layout mismatch (%u vs %u)", off, src.h.total_terms);
     }
     return VS_OK;
@@ -1268,12 +1352,17 @@ static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const 
         GFunctionReg<K> f;
         f.C = 1.0;
         for (int d = 0; d < K; ++d) { f.a[d] = hp[d]; f.C *= hp[K + d]; }
+#ifdef VS_EXP_MINIMAL
+        VS_REQUIRE(second && !sep, VS_ERR_UNSUPPORTED, "experiment build: generic second-order kernel only");
+        return launch_fused_t<K, GFunctionReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
+#else
         if (second) {
             if (sep) return launch_fused_t<K, GFunctionReg<K>, true, true>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
             return launch_fused_t<K, GFunctionReg<K>, true, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
         }
         if (sep) return launch_fused_t<K, GFunctionReg<K>, false, true>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
         return launch_fused_t<K, GFunctionReg<K>, false, false>(c, src, fc, f, i_begin, i_end, partials, req, finalized);
+#endif
     }
     if constexpr (K == 3) {
         if (o.id == VS_OBJ_ISHIGAMI) {

@@ -1,4 +1,5 @@
 // Context, error reporting, scratch management and host-built tables.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -74,6 +75,7 @@ void load_options(Options &o) {
     o.gram_debug = env_int("VS_GRAM_DEBUG", 0);
     o.p2p_timeout_ms = env_int("VS_P2P_TIMEOUT_MS", 10000);
     o.halton_mode = env_int("VS_HALTON_MODE", 0);
+    o.index_bits = env_int("VS_INDEX_BITS", 0);
 }
 
 // Mapped pinned host memory the tail of the fused kernel writes its results to (no device-to-host copy call on the step).
@@ -157,6 +159,43 @@ static void build_terms(const std::vector<uint32_t> &bases, const std::vector<ui
     }
 }
 
+// Constants of the computed-term form (fused_impl.cuh: digit_step_arith) for every (dimension, digit position) a 32-bit
+// index can reach, [k][7]: term(digit) = fma(dd, rh, dd * rl) with dd = 8 * digit.  Returns whether they reproduce the
+// term-table arithmetic of `mode` bit for bit, for every digit of every position (exhaustive).
+static bool build_arith(const std::vector<uint32_t> &bases, int mode, std::vector<double> &arh, std::vector<double> &arl) {
+    const int AJ = 7;
+    arh.assign(bases.size() * AJ, 0.0);
+    arl.assign(bases.size() * AJ, 0.0);
+    bool ok = true;
+    for (size_t d = 0; d < bases.size(); ++d) {
+        volatile double bp = (double)bases[d];
+        volatile double ib = 1.0 / (double)bases[d];
+        volatile double f = ib;
+        for (int j = 0; j < AJ; ++j) {
+            if ((double)bp > 4294967296.0 * (double)bases[d]) break;     // position not reachable by a 32-bit index
+            double rh, rl;
+            if (mode == VS_HALTON_RECIPROCAL) { rh = 1.0 / bp; rl = 0.0; }
+            else if (mode == VS_HALTON_RUNNING_RECIPROCAL) { rh = f; rl = 0.0; }
+            else { rh = 1.0 / bp; rl = std::fma(-rh, (double)bp, 1.0) / bp; }
+            arh[d * AJ + j] = rh * 0.125;
+            arl[d * AJ + j] = rl * 0.125;
+            for (uint32_t digit = 0; digit < bases[d]; ++digit) {
+                volatile double want;
+                if (mode == VS_HALTON_RECIPROCAL) want = (double)digit * (1.0 / bp);
+                else if (mode == VS_HALTON_RUNNING_RECIPROCAL) want = (double)digit * f;
+                else want = (double)digit / bp;
+                const double dd = 8.0 * (double)digit;
+                volatile double t = dd * arl[d * AJ + j];
+                const double got = std::fma(dd, arh[d * AJ + j], (double)t);
+                if (got != (double)want) ok = false;
+            }
+            bp = bp * (double)bases[d];
+            f = f * ib;
+        }
+    }
+    return ok;
+}
+
 int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
     VS_REQUIRE(max_index < (1ull << 32), VS_ERR_RANGE, "Halton index %llu does not fit 32 bits",
                (unsigned long long)max_index);
@@ -199,6 +238,7 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         hc.k = k;
         hc.mode = mode;
         hc.ndigits = nd;
+        hc.arith_ok = build_arith(bases, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, hc.arh, hc.arl);
     }
     hc.dev.mode = mode;
     *out = hc.dev;
@@ -410,6 +450,14 @@ extern "C" int vs_ctx_set_halton_mode(vs_ctx *c, int mode) {
     return VS_OK;
 }
 
+extern "C" int vs_halton_arith_check(int k, int mode) {
+    if (k <= 0 || mode < VS_HALTON_DIVIDE || mode > VS_HALTON_RUNNING_RECIPROCAL) return -1;
+    std::vector<uint32_t> bases;
+    std::vector<double> arh, arl;
+    first_primes(k, bases);
+    return build_arith(bases, mode, arh, arl) ? 1 : 0;
+}
+
 extern "C" int vs_halton_terms(int k, uint64_t max_index, uint32_t *ndigits, uint32_t *offsets, double *terms,
                                uint64_t capacity, uint64_t *count) {
     return vs_halton_terms_mode(k, max_index, VS_HALTON_DIVIDE, ndigits, offsets, terms, capacity, count);
@@ -432,6 +480,86 @@ extern "C" int vs_halton_terms_mode(int k, uint64_t max_index, int mode, uint32_
         VS_REQUIRE(capacity >= t.size(), VS_ERR_ARG, "terms capacity %llu < %zu", (unsigned long long)capacity, t.size());
         memcpy(terms, t.data(), sizeof(double) * t.size());
     }
+    return VS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numpy.random.seed(s); numpy.random.shuffle(M_2)   (varsens/saltelli.py:100-101) as a row permutation.
+// numpy's legacy global RNG is MT19937 seeded with init_genrand(s); shuffle walks i = n-1 .. 1 and swaps row i with row
+// j = rk_interval(i): the smallest all-ones mask >= i, 32-bit draws AND-ed with it until the value is <= i.  The draws do
+// not depend on the data, so they are produced a block ahead and the cache lines they will touch are prefetched -- the
+// walk itself is a chain of random accesses into a 4n-byte array (64 MB at n = 2^24) and otherwise pays a full miss per
+// swap.  key/pos give numpy's generator state AFTER the shuffle (the reference leaves the global RNG there).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MT19937 {
+    uint32_t key[624];
+    int pos;
+    void seed(uint32_t s) {                                   // init_genrand (numpy: mt19937_seed)
+        for (int i = 0; i < 624; ++i) {
+            key[i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+        }
+        pos = 624;
+    }
+    void gen() {
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < 624 - 397; ++kk) {
+            y = (key[kk] & UPPER) | (key[kk + 1] & LOWER);
+            key[kk] = key[kk + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+        }
+        for (; kk < 623; ++kk) {
+            y = (key[kk] & UPPER) | (key[kk + 1] & LOWER);
+            key[kk] = key[kk + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+        }
+        y = (key[623] & UPPER) | (key[0] & LOWER);
+        key[623] = key[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+        pos = 0;
+    }
+    inline uint32_t next() {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+};
+}  // namespace
+
+extern "C" int vs_reference_permutation(uint64_t n, uint32_t seed, uint32_t *perm, uint32_t *key_out, int *pos_out) {
+    VS_REQUIRE(perm || n == 0, VS_ERR_ARG, "perm is NULL");
+    VS_REQUIRE(n <= 0xffffffffull, VS_ERR_RANGE, "n does not fit 32 bits");
+    MT19937 mt;
+    mt.seed(seed);
+    for (uint64_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+    constexpr int AHEAD = 64;                                // draws produced (and lines prefetched) ahead of the swaps
+    uint32_t js[AHEAD];
+    uint64_t i = n > 0 ? n - 1 : 0;
+    while (i >= 1) {
+        const int cnt = (int)(i < (uint64_t)AHEAD ? i : (uint64_t)AHEAD);
+        for (int u = 0; u < cnt; ++u) {
+            const uint32_t mx = (uint32_t)(i - (uint64_t)u);
+            uint32_t mask = mx;                               // smallest all-ones mask >= mx
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            uint32_t v;
+            while ((v = (mt.next() & mask)) > mx) {}
+            js[u] = v;
+            __builtin_prefetch(perm + v, 1, 0);
+        }
+        for (int u = 0; u < cnt; ++u) {
+            const uint64_t ii = i - (uint64_t)u;
+            const uint32_t j = js[u], t = perm[ii];
+            perm[ii] = perm[j];
+            perm[j] = t;
+        }
+        i -= (uint64_t)cnt;
+    }
+    if (key_out) memcpy(key_out, mt.key, sizeof(mt.key));
+    if (pos_out) *pos_out = mt.pos;
     return VS_OK;
 }
 

@@ -4,7 +4,13 @@
 
 namespace vs {
 
+// VS_FUSED_EXP_K=<k>: experiment builds with a single k (make exp K=<k> TAG=<name> EXTRA=...)
+#ifdef VS_FUSED_EXP_K
+#define VS_EXPAND_X(X, KK) X(KK)
+#define VS_FUSED_K_LIST(X) VS_EXPAND_X(X, VS_FUSED_EXP_K)
+#else
 #define VS_FUSED_K_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20)
+#endif
 
 #define VS_DECLARE(KK)                                                                                                         \
     int launch_fused_k##KK(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o, uint64_t i_begin, \

@@ -99,6 +99,10 @@ struct HaltonCache {
     int k = 0;
     int mode = 0;
     std::vector<uint32_t> ndigits;
+    // double-double reciprocals for computed terms (fused_impl.cuh: digit_step_arith), [k][7], and whether they reproduce
+    // every entry of the term table bit for bit (checked when the table is built)
+    std::vector<double> arh, arl;
+    bool arith_ok = false;
     HaltonDev dev{};
     void *blob = nullptr;
 };
@@ -115,7 +119,7 @@ struct Options {
     int gram_st = 0, gram_rc = 0, gram_stages = 0, gram_hint = 0x989680, gram_debug = 0;
     int p2p_timeout_ms = 10000; // VS_P2P_TIMEOUT_MS bounded wait for the peers' flags in the exchange
     int halton_mode = 0;        // VS_HALTON_MODE    term-table arithmetic (enum vs_halton_mode)
-    int eg = 0;                 // reserved
+    int index_bits = 0;         // VS_INDEX_BITS=32 forces the general (32-bit index) fused kernel
 };
 
 // What the tail of the fused kernel has to do after the CTA partial sums are complete (host side of FusedTail).

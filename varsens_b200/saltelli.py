@@ -26,23 +26,22 @@ _perm_cache = {}          # n -> (uint32 permutation, global numpy RNG state aft
 
 
 def _reference_permutation(n):
-    """The row order ``numpy.random.seed(1); numpy.random.shuffle(M_2)`` produces (saltelli.py:100-101),
-    drawn from the same global legacy RNG with the same side effect on its state.  The order depends on n only
-    (the seed is fixed), and the Fisher-Yates walk is serial (~1 s at n = 2^24, 200x the GPU work that follows), so
-    the last few permutations are kept; a cache hit restores the RNG state the reference call would have left."""
+    """The row order ``numpy.random.seed(1); numpy.random.shuffle(M_2)`` produces (saltelli.py:100-101), with the same side
+    effect on numpy's global legacy RNG.  The Fisher-Yates walk is serial: numpy needs ~1 s for n = 2^24 (200x the GPU work
+    that follows), the library's own MT19937 walk with look-ahead prefetching (vs_reference_permutation, bit-identical to
+    numpy, tests/test_cabi_host.py) a fraction of that.  The order depends on n only (the seed is fixed), so the last few
+    permutations are kept; a cache hit restores the RNG state the reference call would have left."""
     n = int(n)
     hit = _perm_cache.get(n)
     if hit is not None:
         numpy.random.set_state(hit[1])
         return hit[0]
-    idx = numpy.arange(n)
-    numpy.random.seed(1)
-    numpy.random.shuffle(idx)
-    perm = idx.astype(numpy.uint32)
+    perm, state = _cabi.reference_permutation(n, 1)
+    numpy.random.set_state(state)
     perm.setflags(write=False)
     while len(_perm_cache) >= 4:
         _perm_cache.pop(next(iter(_perm_cache)))
-    _perm_cache[n] = (perm, numpy.random.get_state())
+    _perm_cache[n] = (perm, state)
     return perm
 
 
