@@ -222,8 +222,45 @@ __device__ __forceinline__ void load_fixed_table(double *__restrict__ dst, const
 // tools/check_fastdiv.py): c = ceil(2^32 / b);  m*c as a 64-bit product gives q = hi and, from the low word,
 // 8*(m mod b) = umulhi(lo, 8b) -- two multiplies, no shift, no subtraction, and the result is already the byte
 // offset into the row.  GENERAL form: the compiler's division by a constant.
-template <uint32_t B, bool FAST>
-__device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *__restrict__ row) {
+// Addressing: the term is read with ld.shared [addr + rowoff], rowoff an immediate and addr = 8*(m mod b) + base of the table
+// in the shared window.  The base is carried as the HIGH word of a 64-bit addend (`basehi`, kept opaque and live for the
+// whole kernel), so that the second multiply delivers the address directly: IMAD.HI(lo, 8b, basehi) = umulhi(lo, 8b) + base.
+// (The compiler found that form by itself but re-built the {0, base} register pair with two moves for every step -- 270
+// IMAD.MOV per 32 rows in the ncu source view of the first single-launch build, profiles/r02_fused_stalls_by_line.txt.)
+// FIRST: the first term initialises the sum (0.0 + t == t for the non-negative table terms; saves a DADD per coordinate).
+#ifndef VS_ADDR_MODE
+#define VS_ADDR_MODE 4
+#endif
+template <uint32_t B, bool FAST, bool FIRST, uint32_t ROWOFF>
+__device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *__restrict__ tb, uint64_t basehi) {
+    double t;
+#if VS_ADDR_MODE == 4
+    // The whole step in PTX, so that exactly these instructions come out: IMAD.WIDE (m * c), IMAD.HI with the persistent
+    // {0, base} pair as addend (address of the term), LDS with the row offset as immediate, and the DADD.  (Written in C++ the
+    // compiler decomposed the 64-bit product, added a uniform zero to the high word and masked low bits of the low word --
+    // one or two extra instructions per step.)
+    (void)tb;
+    if constexpr (FAST) {
+        constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
+        asm("{\n\t"
+            ".reg .b64 w, a;\n\t"
+            ".reg .b32 lo, ah, dm;\n\t"
+            "mul.wide.u32 w, %1, %3;\n\t"
+            "mov.b64 {lo, %1}, w;\n\t"
+            "mul.wide.u32 a, lo, %4;\n\t"
+            "add.u64 a, a, %2;\n\t"
+            "shr.u64 a, a, 32;\n\t"
+            "ld.shared.f64 %0, [a+%5];\n\t"
+            "}"
+            : "=d"(t), "+r"(m)
+            : "l"(basehi), "n"(C), "n"(8u * B), "n"(ROWOFF));
+    } else {
+        const uint32_t q = m / B;
+        const uint32_t addr = (m - q * B) * 8u + (uint32_t)(basehi >> 32);
+        m = q;
+        asm("ld.shared.f64 %0, [%1+%2];" : "=d"(t) : "l"((uint64_t)addr), "n"(ROWOFF));
+    }
+#elif VS_ADDR_MODE == 0
     uint32_t off8;
     if constexpr (FAST) {
         constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
@@ -235,7 +272,43 @@ __device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *_
         off8 = (m - q * B) * 8u;
         m = q;
     }
-    x = __dadd_rn(x, *reinterpret_cast<const double *>(row + off8));
+    (void)basehi;
+    t = *reinterpret_cast<const double *>(tb + ROWOFF + off8);
+#elif VS_ADDR_MODE == 1 || VS_ADDR_MODE == 2
+    uint32_t addr;
+    if constexpr (FAST) {
+        constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
+        const uint64_t w = (uint64_t)m * C;
+        addr = (uint32_t)(((uint64_t)(uint32_t)w * (uint64_t)(8u * B) + basehi) >> 32);
+        m = (uint32_t)(w >> 32);
+    } else {
+        const uint32_t q = m / B;
+        addr = (m - q * B) * 8u + (uint32_t)(basehi >> 32);
+        m = q;
+    }
+    (void)tb;
+#if VS_ADDR_MODE == 1
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(t) : "l"((uint64_t)addr), "n"(ROWOFF));
+#else
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(t) : "r"(addr), "n"(ROWOFF));
+#endif
+#else
+    uint32_t off8;
+    if constexpr (FAST) {
+        constexpr uint32_t C = (uint32_t)((0x100000000ull + B - 1) / B);
+        const uint64_t w = (uint64_t)m * C;
+        off8 = __umulhi((uint32_t)w, 8u * B);
+        m = (uint32_t)(w >> 32);
+    } else {
+        const uint32_t q = m / B;
+        off8 = (m - q * B) * 8u;
+        m = q;
+    }
+    (void)tb;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(t) : "l"((basehi >> 32) + (uint64_t)off8), "n"(ROWOFF));
+#endif
+    if constexpr (FIRST) x = t;
+    else x = __dadd_rn(x, t);
 }
 
 // The same step with the term COMPUTED instead of looked up (B-points of bases >= 37, whose table rows span more than the
@@ -247,7 +320,7 @@ __device__ __forceinline__ void digit_step(uint32_t &m, double &x, const char *_
 // result IS the correctly rounded quotient; on top of the argument the host compares all digits of all positions against
 // the term table when the constants are built (host.cu: build_arith) and refuses the fused kernel on any mismatch.
 // The other term-table modes use rl = 0 and rh = their factor: the same instruction sequence gives RN(digit * factor).
-template <uint32_t B, bool FAST>
+template <uint32_t B, bool FAST, bool FIRST>
 __device__ __forceinline__ void digit_step_arith(uint32_t &m, double &x, double rh, double rl) {
     uint32_t off8;
     if constexpr (FAST) {
@@ -261,7 +334,9 @@ __device__ __forceinline__ void digit_step_arith(uint32_t &m, double &x, double 
         m = q;
     }
     const double dd = __dadd_rn(__hiloint2double(0x43300000, (int)off8), -4503599627370496.0);
-    x = __dadd_rn(x, __fma_rn(dd, rh, __dmul_rn(dd, rl)));
+    const double t = __fma_rn(dd, rh, __dmul_rn(dd, rl));
+    if constexpr (FIRST) x = t;
+    else x = __dadd_rn(x, t);
 }
 
 // Halton digit sums of the two indices ia (A_i) and ib (B_i) for one GROUP of HG dimensions: 2*HG independent
@@ -276,8 +351,8 @@ template <int K>
 __host__ __device__ constexpr int halton_groups() { return K > 1 ? (K - 1 + HG - 1) / HG : 1; }
 
 template <int K, int SCALE, int G, int IB, class Emit>
-__device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const double *__restrict__ terms, uint32_t ia, uint32_t ib,
-                                             Emit &&emit) {
+__device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const double *__restrict__ terms, uint64_t basehi, uint32_t ia,
+                                             uint32_t ib, Emit &&emit) {
     if constexpr (G == 0)
         emit(0, scale_coord<K, SCALE>(fc, 0, (double)__brev(ia) * 2.3283064365386962890625e-10),
              scale_coord<K, SCALE>(fc, 0, (double)__brev(ib) * 2.3283064365386962890625e-10));
@@ -311,25 +386,26 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
                     constexpr int U = decltype(Uc)::value;
                     constexpr uint32_t B = prime_at(D0 + U);
                     if constexpr (J < nd_ib<IB>(B)) {
-                        const char *row = tb + (size_t)(foff(D0 + U) + J * B) * 8;
+                        constexpr uint32_t RO = (uint32_t)(foff(D0 + U) + J * B) * 8u;   // byte offset of the row inside the table
                         constexpr bool AR = (D0 + U) >= AR_D0;               // B-point term computed, not looked up
                         constexpr int AU = AR ? (D0 + U - AR_D0) : 0, AJ = J < AR_J ? J : AR_J - 1;
-                        if constexpr (J == 0) {
-                            digit_step<B, false>(ma[U], xa[U], row);
-                            if constexpr (AR) digit_step_arith<B, false>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
-                            else digit_step<B, false>(mb[U], xb[U], row);
-                        } else if constexpr (J >= jfast(B) || IB <= 29) {
-                            digit_step<B, true>(ma[U], xa[U], row);
-                            if constexpr (AR) digit_step_arith<B, true>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
-                            else digit_step<B, true>(mb[U], xb[U], row);
+                        constexpr bool F1 = J == 0;
+                        if constexpr (J == 0 && !(IB <= 29 && 8ull * B * ((1ull << (IB < 32 ? IB : 31))) <= 0x100000000ull)) {
+                            digit_step<B, false, F1, RO>(ma[U], xa[U], tb, basehi);
+                            if constexpr (AR) digit_step_arith<B, false, F1>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, false, F1, RO>(mb[U], xb[U], tb, basehi);
+                        } else if constexpr (J == 0 || J >= jfast(B) || IB <= 29) {
+                            digit_step<B, true, F1, RO>(ma[U], xa[U], tb, basehi);
+                            if constexpr (AR) digit_step_arith<B, true, F1>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, true, F1, RO>(mb[U], xb[U], tb, basehi);
                         } else if (small) {
-                            digit_step<B, true>(ma[U], xa[U], row);
-                            if constexpr (AR) digit_step_arith<B, true>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
-                            else digit_step<B, true>(mb[U], xb[U], row);
+                            digit_step<B, true, F1, RO>(ma[U], xa[U], tb, basehi);
+                            if constexpr (AR) digit_step_arith<B, true, F1>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, true, F1, RO>(mb[U], xb[U], tb, basehi);
                         } else {
-                            digit_step<B, false>(ma[U], xa[U], row);
-                            if constexpr (AR) digit_step_arith<B, false>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
-                            else digit_step<B, false>(mb[U], xb[U], row);
+                            digit_step<B, false, F1, RO>(ma[U], xa[U], tb, basehi);
+                            if constexpr (AR) digit_step_arith<B, false, F1>(mb[U], xb[U], fc.arh[AU][AJ], fc.arl[AU][AJ]);
+                            else digit_step<B, false, F1, RO>(mb[U], xb[U], tb, basehi);
                         }
                     }
                 });
@@ -342,7 +418,7 @@ __device__ __forceinline__ void halton_group(const FusedConst<K> &fc, const doub
 
 template <int K, int SCALE, int IB, class Emit>
 __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
-                                         uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
+                                         uint64_t basehi, uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
     uint64_t r = bt * 32 + lane;
     const bool valid = r < rows;
     const uint64_t i = i_begin + (valid ? r : rows - 1);
@@ -353,7 +429,7 @@ __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedC
         for (int d = 0; d < K; ++d) emit(d, scale_coord<K, SCALE>(fc, d, ra[d]), scale_coord<K, SCALE>(fc, d, rb[d]));
     } else {
         const uint32_t ia = (uint32_t)(src.start + i), ib = (uint32_t)(src.start + src.n + pi);
-        static_for<halton_groups<K>()>([&](auto Gc) { halton_group<K, SCALE, decltype(Gc)::value, IB>(fc, terms, ia, ib, emit); });
+        static_for<halton_groups<K>()>([&](auto Gc) { halton_group<K, SCALE, decltype(Gc)::value, IB>(fc, terms, basehi, ia, ib, emit); });
     }
     return valid;
 }
@@ -361,10 +437,17 @@ __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedC
 // One warp-uniform branch on the scale kind for the whole row (not one per coordinate).
 template <int K, int IB = 32, class Emit>
 __device__ __forceinline__ bool gen_rows(const SourceDev &src, const FusedConst<K> &fc, const double *__restrict__ terms,
-                                         uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
-    if (fc.scale_kind == VS_SCALE_IDENTITY) return gen_rows_impl<K, VS_SCALE_IDENTITY, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
-    if (fc.scale_kind == VS_SCALE_LINEAR) return gen_rows_impl<K, VS_SCALE_LINEAR, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
-    return gen_rows_impl<K, VS_SCALE_POWER, IB>(src, fc, terms, i_begin, rows, bt, lane, emit);
+                                         uint64_t basehi, uint64_t i_begin, uint64_t rows, uint64_t bt, int lane, Emit &&emit) {
+    if (fc.scale_kind == VS_SCALE_IDENTITY) return gen_rows_impl<K, VS_SCALE_IDENTITY, IB>(src, fc, terms, basehi, i_begin, rows, bt, lane, emit);
+    if (fc.scale_kind == VS_SCALE_LINEAR) return gen_rows_impl<K, VS_SCALE_LINEAR, IB>(src, fc, terms, basehi, i_begin, rows, bt, lane, emit);
+    return gen_rows_impl<K, VS_SCALE_POWER, IB>(src, fc, terms, basehi, i_begin, rows, bt, lane, emit);
+}
+
+// {0, shared-window address of the term table} as one opaque 64-bit value (see digit_step)
+__device__ __forceinline__ uint64_t table_basehi(const double *terms) {
+    uint64_t v = (uint64_t)(uint32_t)__cvta_generic_to_shared(terms) << 32;
+    asm volatile("" : "+l"(v));
+    return v;
 }
 
 // Generic evaluation of EG design points of one base row for a product-form functor (see eval_rows).
@@ -524,7 +607,7 @@ __device__ __forceinline__ void rows_phase(const SourceDev &src, const FusedCons
                                            uint64_t rows, uint64_t bt, int lane, double *__restrict__ Yrow, double shift,
                                            double &sA, double &qA, double &sB, double &qB) {
     double a[K], b[K];
-    const bool valid = gen_rows<K>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+    const bool valid = gen_rows<K>(src, fc, terms, table_basehi(terms), i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
         a[d] = xa;
         b[d] = xb;
     });
@@ -659,6 +742,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of spinning
         : "memory");
+}
+
+// Consumer-side wait with explicit back-off.  try_wait with a suspend hint compiles to a TRYWAIT / NANOSLEEP.SYNCS / BRA loop that
+// still issued ~680 instructions per 32-row batch from the (mostly idle) S-warps -- 14 % of all issued instructions in the ncu
+// capture of the first single-launch build, competing with the E-warps of the same sub-partition for issue slots.  The S-warp has
+// slack (it works ~15 % of the time), so it polls with test_wait and sleeps VS_SBACKOFF ns between polls.
+#ifndef VS_SBACKOFF
+#define VS_SBACKOFF 0
+#endif
+__device__ __forceinline__ void mbar_wait_consumer(uint64_t *bar, uint32_t parity) {
+#if VS_SBACKOFF > 0
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(VS_SBACKOFF);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -993,6 +1104,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 #endif
         const int e = warp - WS_S;
         const double shift = shift_sh;
+        const uint64_t basehi = table_basehi(terms);
         const uint64_t cnt = count_of(e);
         uint64_t bt = (uint64_t)blockIdx.x * WS_E + e;
         // Phase alternation between the two E-warp teams (team = e / WS_S; every sub-partition has one warp of each).
@@ -1028,7 +1140,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 #pragma unroll
                 for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
             } else {
-                valid = gen_rows<K, IB>(src, fc, terms, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
+                valid = gen_rows<K, IB>(src, fc, terms, basehi, i_begin, rows, bt, lane, [&](int d, double xa, double xb) {
                     a[d] = xa;
                     b[d] = xb;
                 });
@@ -1073,7 +1185,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
                 const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 32;
                 long long *trp = fc.trace + ((size_t)warp * 64 + (it < 32 ? it * EPS + h : 0)) * 4;
                 if (tr_on) trp[0] = clock64();
-                mbar_wait(full_bar(e, slot), par);
+                mbar_wait_consumer(full_bar(e, slot), par);
                 if (tr_on) trp[1] = clock64();
                 const double *Y = tiles + ((size_t)e * NBUF + slot) * TILE + foff;
 #pragma unroll 2
