@@ -204,24 +204,24 @@ def run_gpu(args, rank, world):
     exchange = "none" if world == 1 else ("one-launch step: peer-memory all-reduce over NVLink inside the fused kernel" if ex is not None
                                           else "NCCL all_reduce between vs_fused_partials and vs_finalize")
 
-    def step_with(perm, use_ex):
-        """One step = indices of the full design on the host.  N=1: vs_run_fused (one launch).  N>1: vs_run_fused_p2p (one launch
-        per rank, exchange inside the kernel) or, NCCL arm, vs_fused_partials -> all_reduce -> vs_finalize."""
+    # The step through the public API: a prepared plan (Context.fused_plan: arguments converted once) whose run() is ONE foreign
+    # call = one kernel launch per rank.  N=1: vs_run_fused.  N>1: vs_run_fused_p2p (exchange inside the kernel) or, NCCL arm,
+    # vs_fused_partials -> all_reduce -> vs_finalize.
+    def make_step(perm, use_ex):
         if world == 1:
-            return ctx.run_fused(k, n, perm, _cabi.OBJ_GFUNCTION, A, flags=flags)
+            return ctx.fused_plan(k, n, perm, _cabi.OBJ_GFUNCTION, A, flags=flags).run
         if use_ex is not None:
-            return ctx.run_fused_p2p(k, n, perm, _cabi.OBJ_GFUNCTION, A, use_ex.world, use_ex.rank, use_ex.peer_bufs, use_ex.peer_flags,
-                                     use_ex.next_epoch(), lo, hi, flags=flags)
-        ctx.fused_partials(k, n, perm, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
-        vdist.allreduce_partials(part)                                  # same stream as the ctx (set_stream above)
-        return ctx.finalize(k, 1, n, part, flags)
+            return ctx.fused_plan(k, n, perm, _cabi.OBJ_GFUNCTION, A, flags=flags, i_begin=lo, i_end=hi, exchange=use_ex).run
 
-    def step_resident():
-        return step_with(perm_dev, ex)
+        def nccl_step():
+            ctx.fused_partials(k, n, perm, _cabi.OBJ_GFUNCTION, A, i_begin=lo, i_end=hi, flags=flags, out=part)
+            vdist.allreduce_partials(part)                              # same stream as the ctx (set_stream above)
+            return ctx.finalize(k, 1, n, part, flags)
+        return nccl_step
 
-    def step_e2e():
-        # public call with HOST buffers: permutation slice H2D from pinned memory, indices to the host, every step
-        return step_with(perm_host, ex)
+    step_resident = make_step(perm_dev, ex)
+    # public call with HOST buffers: permutation slice H2D from pinned memory, indices to the host, every step
+    step_e2e = make_step(perm_host, ex)
 
     def barrier():
         if world > 1:
@@ -261,17 +261,21 @@ def run_gpu(args, rank, world):
     peak_tflops = ctx.measure_fp64_peak()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launch_count()
-    kernel_ms = []
-    ms, res = timed(step_resident, args.steps, args.warmup, kernel_ms)
+    ms, res = timed(step_resident, args.steps, args.warmup)
     launches = (ctx.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
     tail_ns = ctx.last_tail_ns(k).tolist()
+    # the fused kernel alone: same steps once more with the library's events around the launch switched on
+    kernel_ms = []
+    ctx.set_timing(True)
+    timed(step_resident, max(3, args.steps // 2), 2, kernel_ms)
+    ctx.set_timing(False)
     ms_e2e, res2 = timed(step_e2e, args.steps, max(args.warmup, 3), wall_too=True)
     clocks = sampler.stop() if sampler else None          # sampled over both timed regions
 
     # the other exchange, for the record (N>1): NCCL all_reduce between the partial-sum launch and the finalize launch
     nccl_ms = None
     if world > 1 and ex is not None:
-        nccl_ms, res_nccl = timed(lambda: step_with(perm_dev, None), max(3, args.steps // 2), 3)
+        nccl_ms, res_nccl = timed(make_step(perm_dev, None), max(3, args.steps // 2), 3)
         nccl_same = bool(numpy.allclose(res_nccl.sens, res.sens, rtol=1e-12, atol=1e-14))
 
     # index time: from "partial sums of every rank ready" to the indices on the host
@@ -387,6 +391,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION prints there otherwise)
+    # stdout carries exactly ONE JSON line: whatever a library prints there meanwhile (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         return run_reference(args, rank)
     if args.warmup < 3:

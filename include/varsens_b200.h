@@ -223,8 +223,10 @@ int vs_run_fused_p2p(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uin
 /* ---- measurement helpers --------------------------------------------------------------------------- */
 /* DFMA-chain microbenchmark: returns measured FP64 TFLOP/s (FMA = 2 flops) of this GPU in *tflops. */
 int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops);
-/* Device time in ms of the last vs_fused_partials / vs_eval_values / vs_partials_from_values /
- * vs_sample_flat main kernel, from CUDA events recorded on the ctx stream. */
+/* Device time in ms of the last vs_fused_partials / vs_run_fused / vs_eval_values / vs_partials_from_values /
+ * vs_sample_flat main kernel, from CUDA events recorded on the ctx stream around the launch.  The events are only recorded
+ * while timing is switched on (off by default: two event records are ~4 us of host time per call). */
+int vs_ctx_set_timing(vs_ctx *ctx, int on);
 int vs_last_kernel_ms(vs_ctx *ctx, float *ms);
 /* Time stamps (ns, %globaltimer) of the tail of the last one-launch fused step with estimators (vs_run_fused /
  * vs_run_fused_p2p, k factors): ns4 = {combine + pack, peer stores + fence + flags, wait for the peers, rank-order sum +

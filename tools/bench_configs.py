@@ -8,6 +8,7 @@ import varsens_b200 as vb
 from varsens_b200 import _cabi
 
 ctx = vb.Context.get(0)
+ctx.set_timing(True)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 dev = torch.device("cuda", 0)
 out = {"gpu": torch.cuda.get_device_name(0)}

@@ -10,6 +10,7 @@ k = int(os.environ.get("VS_K", "20"))
 n = 1 << int(os.environ.get("VS_LOGN", "24"))
 a = ([0, .5, 3, 9, 99, 99] + [99.0] * 14)[:k]
 ctx = vb.Context.get(0)
+ctx.set_timing(True)
 perm = torch.from_numpy(saltelli._reference_permutation(n).astype(numpy.int32)).cuda()
 flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
 ts, res = [], None

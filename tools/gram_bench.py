@@ -24,6 +24,7 @@ def main():
         pass
     hbm = float(peaks.get("hbm_gbs", 6388.0))
     ctx = Context(0)
+    ctx.set_timing(True)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
     for k, rows, l in CONFIGS:
         m = (2 + 2 * k) * l

@@ -4,6 +4,7 @@ import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from varsens_b200 import Context
 ctx = Context(0)
+ctx.set_timing(True)
 k, rows = int(sys.argv[1]), 1 << int(sys.argv[2])
 m = 2 + 2 * k
 vals = torch.rand(m * rows, dtype=torch.float64, device="cuda") + 1.0

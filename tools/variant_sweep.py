@@ -4,6 +4,7 @@ sys.path.insert(0, os.getcwd())
 import varsens_b200 as vb
 from varsens_b200 import _cabi
 ctx = vb.Context.get(0)
+ctx.set_timing(True)
 n = 1 << 23
 perm = torch.from_numpy(numpy.random.RandomState(1).permutation(n).astype(numpy.int32)).cuda()
 for k in (4, 6, 8, 10, 11, 12, 14, 15, 16, 18, 20):

@@ -25,7 +25,7 @@ SYMBOLS = (
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
     "vs_finalize_device", "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
     "vs_ctx_reload_env", "vs_ctx_set_halton_mode", "vs_halton_terms_mode", "vs_run_fused_p2p", "vs_last_tail_ns",
-    "vs_halton_arith_check", "vs_reference_permutation",
+    "vs_halton_arith_check", "vs_reference_permutation", "vs_ctx_set_timing",
 )
 HALTON_DIVIDE, HALTON_RECIPROCAL, HALTON_RUNNING_RECIPROCAL, HALTON_HORNER = 0, 1, 2, 3
 ERR_TIMEOUT = 6
@@ -92,6 +92,7 @@ def lib():
         L.vs_halton_terms_mode.argtypes = [i32, u64, i32, vp, vp, vp, u64, P(u64)]
         L.vs_last_tail_ns.argtypes = [vp, i32, vp]
         L.vs_halton_arith_check.argtypes = [i32, i32]
+        L.vs_ctx_set_timing.argtypes = [vp, i32]
         L.vs_reference_permutation.argtypes = [u64, ctypes.c_uint32, vp, vp, P(i32)]
         L.vs_measure_fp64_peak.argtypes = [vp, P(ctypes.c_double)]
         L.vs_last_kernel_ms.argtypes = [vp, P(ctypes.c_float)]
@@ -179,6 +180,26 @@ class Result(object):
         self.sens_2 = numpy.zeros((k, l, k, l)) if second_order else None
         self.sens_2n = numpy.zeros((k, l, k, l)) if second_order else None
 
+    @classmethod
+    def views(cls, k, l, flat, second_order=True):
+        """Result whose arrays are views of one flat float64 buffer in the library's result order (no copies)."""
+        r = cls.__new__(cls)
+        r.k, r.l = k, l
+        kl = k * l
+        r.E_2, r.var_y = flat[0:l], flat[l:2 * l]
+        at = 2 * l
+        r.U_j = flat[at:at + kl].reshape(k, l)
+        r.U_nj = flat[at + kl:at + 2 * kl].reshape(k, l)
+        r.sens = flat[at + 2 * kl:at + 3 * kl].reshape(k, l)
+        r.sens_t = flat[at + 3 * kl:at + 4 * kl].reshape(k, l)
+        at += 4 * kl
+        if second_order:
+            r.sens_2 = flat[at:at + kl * kl].reshape(k, l, k, l)
+            r.sens_2n = flat[at + kl * kl:at + 2 * kl * kl].reshape(k, l, k, l)
+        else:
+            r.sens_2 = r.sens_2n = None
+        return r
+
     @staticmethod
     def flat_len(k, l):
         return 2 * l + 4 * k * l + 2 * (k * l) ** 2
@@ -260,6 +281,10 @@ class Context(object):
 
     def launch_count(self):
         return int(lib().vs_ctx_launch_count(self._h))
+
+    def set_timing(self, on=True):
+        """Record CUDA events around the main kernel of each call (read them with last_kernel_ms); off by default."""
+        check(lib().vs_ctx_set_timing(self._h, int(bool(on))))
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()
@@ -412,6 +437,63 @@ def _run_fused_p2p(self, k, n, perm, objective, params, world_size, rank, peer_b
 
 
 Context.run_fused_p2p = _run_fused_p2p
+
+
+class FusedPlan(object):
+    """A prepared fused step: every argument of vs_run_fused / vs_run_fused_p2p converted once (ctypes pointers, descriptor
+    structs, peer tables), so that ``run()`` costs one foreign call -- the per-step host overhead matters once the GPU work is
+    ~0.6 ms (8-GPU strong scaling of BASELINE config 3).  ``exchange`` = a dist.PeerExchange for the multi-GPU one-launch step
+    (rows [i_begin, i_end) are this rank's shard), None for a single GPU.  The buffers passed in must stay alive and unchanged
+    while the plan is used."""
+
+    def __init__(self, ctx, k, n, perm, objective, params, discard=0, scale=IDENTITY, raw=None, flags=FLAG_SECOND_ORDER,
+                 i_begin=0, i_end=None, exchange=None):
+        self.ctx, self.k, self.second = ctx, int(k), bool(flags & FLAG_SECOND_ORDER)
+        self.exchange = exchange
+        par = numpy.ascontiguousarray(params, dtype=numpy.float64)
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        self._keep = (par, keep, pk, rk, sp)
+        self._len = Result.flat_len(self.k, 1) if self.second else 2 + 4 * self.k
+        kk = self.k
+        self._offsets = (0, 1, 2, 2 + kk, 2 + 2 * kk, 2 + 3 * kk, 2 + 4 * kk, 2 + 4 * kk + kk * kk)
+        L = lib()
+        i_end = n if i_end is None else i_end
+        if exchange is None:
+            if i_begin != 0 or i_end != n:
+                raise VarsensError("a single-GPU plan covers the whole design")
+            self._fn = L.vs_run_fused
+            self._args = (ctx._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                          par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(flags))
+        else:
+            pb = (ctypes.c_uint64 * exchange.world)(*[int(x) for x in exchange.peer_bufs])
+            pf = (ctypes.c_uint64 * exchange.world)(*[int(x) for x in exchange.peer_flags])
+            self._keep += (pb, pf)
+            self._fn = L.vs_run_fused_p2p
+            self._args = (ctx._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(objective),
+                          par.ctypes.data_as(ctypes.c_void_p), int(par.size), int(i_begin), int(i_end), int(flags),
+                          int(exchange.world), int(exchange.rank), pb, pf)
+
+    def run(self):
+        flat = numpy.empty(self._len)
+        base = flat.ctypes.data
+        o = self._offsets
+        if self.second:
+            cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5],
+                           base + 8 * o[6], base + 8 * o[7])
+        else:
+            cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5], None, None)
+        if self.exchange is None:
+            st = self._fn(*self._args, ctypes.byref(cs))
+        else:
+            st = self._fn(*self._args, self.exchange.next_epoch(), ctypes.byref(cs))
+        if st != VS_OK:
+            check(st)
+        return Result.views(self.k, 1, flat, self.second)
+
+
+Context.fused_plan = lambda self, *a, **kw: FusedPlan(self, *a, **kw)
 
 
 def reference_permutation(n, seed=1):

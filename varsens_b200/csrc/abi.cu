@@ -248,10 +248,10 @@ extern "C" int vs_indices_from_values(vs_ctx *c, int k, int l, uint64_t n, uint6
 // combine by the last CTA, and -- depending on FusedReq::mode -- the packed partial sums, the estimators, or the
 // peer-memory all-reduce followed by the estimators, with the results written to mapped host memory.
 //
-// Host permutation (VS_MEM_HOST): the H2D copy (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over PCIe) is cut into
-// growing slices on the copy stream, each followed by an 8-byte copy that bumps an arrival counter in HBM; the SAME single
-// launch polls that counter before it touches a slice, so only the first small slice is exposed and no launch is repeated.
-// The copies are enqueued before the launch (a serialising tool -- compute-sanitizer, CUDA_LAUNCH_BLOCKING -- cannot deadlock).
+// Host permutation (VS_MEM_HOST): the H2D copy (4 bytes per base row: 64 MB at n = 2^24, ~1.2 ms over PCIe) is ONE
+// cudaMemcpyAsync on the copy stream into a staging buffer whose entries hold a sentinel; the SAME single launch runs while the
+// bytes arrive -- every lane polls its own entry -- so only the first few hundred KB are exposed and no launch is repeated.
+// The copy is enqueued before the launch (a serialising tool -- compute-sanitizer, CUDA_LAUNCH_BLOCKING -- cannot deadlock).
 // ---------------------------------------------------------------------------------------------------------------------
 static const uint64_t PIPE_MIN_ROWS = 1ull << 19;
 
@@ -267,50 +267,30 @@ static int fused_step(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint
     SourceDev src;
     if (perm_mem == VS_MEM_HOST && !raw && tail_ok && rows >= PIPE_MIN_ROWS && !capturing(c) && !c->opt.no_pipeline) {
         VS_REQUIRE(perm, VS_ERR_ARG, "perm is NULL");
-        // slice boundaries in 32-row batches (a batch is one 128-byte line of the staged permutation)
-        static const int cuts64[] = {1, 4, 12, 24, 40, 64};                    // 64ths of the batches: growing slices
-        const uint64_t nbatch = (rows + 31) / 32;
-        int nchunk = 0;
-        uint64_t prev = 0;
-        for (int ci = 0; ci < 6; ++ci) {
-            uint64_t e = ci == 5 ? nbatch : nbatch * (uint64_t)cuts64[ci] / 64;
-            if (e <= prev) continue;
-            req->chunk_end_batch[nchunk++] = (uint32_t)e;
-            prev = e;
+        // Staging buffer whose entries hold the sentinel 0xFFFFFFFF between calls: ONE asynchronous copy is enqueued (before the
+        // launch, so a serialising tool cannot deadlock), the kernel's lanes poll their own entries and put the sentinel back.
+        if (c->poll_buf.cap < rows * sizeof(uint32_t) || !c->poll_clean) {
+            VS_TRY(ensure(c, c->poll_buf, rows * sizeof(uint32_t)));
+            VS_CUDA(cudaMemsetAsync(c->poll_buf.p, 0xFF, c->poll_buf.cap, c->stream));
         }
-        req->nchunk = nchunk;
-        VS_TRY(ensure(c, c->perm_buf, rows * sizeof(uint32_t)));
-        if (!c->ticket_buf.p) {
-            VS_TRY(ensure(c, c->ticket_buf, 256));
-            VS_CUDA(cudaMemsetAsync(c->ticket_buf.p, 0, 256, c->stream));
-        }
+        c->poll_clean = false;                                                  // until the launch below is enqueued
         if (c->pipe_ev.empty()) {
             cudaEvent_t e;
             VS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c->pipe_ev.push_back(e);
         }
-        const uint32_t *perm_dev = (const uint32_t *)c->perm_buf.p - i_begin;      // indexed by the absolute base row
+        const uint32_t *perm_dev = (const uint32_t *)c->poll_buf.p - i_begin;      // indexed by the absolute base row
         VS_TRY(make_source(c, k, n, discard, perm_dev, VS_MEM_DEVICE, i_begin, rows, nullptr, VS_MEM_HOST, &src));
         VS_TRY(get_scale(c, k, scale, &s));
         VS_TRY(get_objective(c, k, objective, params, n_params, &od));
-        // the copies may not overwrite the staging buffer (or the counter) before earlier work on the compute stream is done
+        // the copy may not start before earlier work on the compute stream (the previous kernel's sentinel stores, the refill)
         VS_CUDA(cudaEventRecord(c->pipe_ev[0], c->stream));
         VS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[0], 0));
-        unsigned long long *arrive = (unsigned long long *)((char *)c->ticket_buf.p + 64);
-        req->arrive_dev = arrive;
-        req->arrive_base = c->seq;
-        uint64_t b0 = 0;
-        for (int ch = 0; ch < nchunk; ++ch) {
-            uint64_t b1 = (uint64_t)req->chunk_end_batch[ch] * 32;
-            if (b1 > rows) b1 = rows;
-            VS_CUDA(cudaMemcpyAsync((uint32_t *)c->perm_buf.p + b0, perm + i_begin + b0, (b1 - b0) * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice, c->copy_stream));
-            unsigned long long *slot = c->host_seq + (c->seq % 64);
-            *slot = ++c->seq;
-            VS_CUDA(cudaMemcpyAsync(arrive, slot, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->copy_stream));
-            b0 = b1;
-        }
-        return launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev, req, finalized);
+        VS_CUDA(cudaMemcpyAsync(c->poll_buf.p, perm + i_begin, rows * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+        req->poll_perm = 1;
+        VS_TRY(launch_fused(c, k, src, s, od, i_begin, i_end, flags, partials_dev, req, finalized));
+        c->poll_clean = true;                                                   // the kernel leaves every entry it read at the sentinel
+        return VS_OK;
     }
     VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, rows, raw, raw_mem, &src));
     VS_TRY(get_scale(c, k, scale, &s));

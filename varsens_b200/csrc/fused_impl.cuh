@@ -54,18 +54,19 @@ struct FusedConst {            // kernel parameter -> constant bank; indexed wit
     uint32_t nd[K];            // digits to sum for the largest index of the run
     uint32_t ndc[K];           // digit rows the cached global table holds per dimension (layout: toff)
     int small_index;           // every Halton index of the run is < 2^29
+    int poll_perm;             // see FusedTail::poll_perm
     int alternate;             // (EPS == 2) E-warp teams alternate generate / evaluate phases -- measured slower, off
     long long *trace;          // profiling only (VS_TRACE): per-warp clock stamps of CTA 0, else nullptr
     int scale_kind;
     int debug;                 // profiling only (VS_DEBUG_SKIP): bit 0 = skip generation, bit 1 = skip evaluation
 };
 
-// Everything the LAST CTA of the fused kernel does once all CTA partial sums are in HBM (one launch per step): fixed-order
-// combine, packed partial-sum vector, optional peer-memory all-reduce over NVLink, estimators, results to device and to
-// mapped host memory.  Also carries the arrival flags of a host permutation that is still being copied while the kernel runs.
+// Everything the fused kernel does once the CTA partial sums are in HBM (one launch per step): two-level fixed-order combine
+// (the last CTA of every group of TAIL_GROUP CTAs sums its group, the last of those sums the groups), packed partial-sum
+// vector, optional peer-memory all-reduce over NVLink, estimators, results to device and to mapped host memory.
 struct FusedTail {
     double *blockpart;               // [gridDim.x][LROW] compact CTA partial sums
-    unsigned *ticket;                // CTA completion counter (reset by the last CTA)
+    unsigned *ticket;                // [0] group completion counter, [1 + g] CTA completion counter of group g (reset after use)
     double *partials;                // out: packed partial-sum vector (device) or nullptr
     double *res_dev;                 // out: result vector (device) or nullptr          } mode >= 1
     double *res_host;                // out: result vector + status + time stamps in mapped pinned host memory or nullptr
@@ -75,11 +76,13 @@ struct FusedTail {
     unsigned epoch;
     const uint64_t *peer_bufs, *peer_flags;     // device arrays [world]: every rank's exchange buffer / flag array as mapped here
     unsigned long long timeout_ns;   // bounded wait for the peers
-    const unsigned long long *arrive;           // chunk c of the permutation is in HBM when *arrive >= arrive_base + c + 1
-    unsigned long long arrive_base;
-    int nchunk;
-    uint32_t chunk_end_batch[16];    // first 32-row batch (relative to i_begin) NOT covered by chunks 0..c
+    double *grouppart;               // [ceil(gridDim.x / TAIL_GROUP)][LROW] second-level partial sums
+    int poll_perm;                   // the permutation is being copied into its staging buffer WHILE the kernel runs: entries still
+                                     // hold the sentinel 0xFFFFFFFF until their bytes land; every lane polls its own entry and
+                                     // puts the sentinel back after reading it (the buffer is clean again when the kernel ends)
 };
+constexpr int TAIL_GROUP = 16;       // CTAs per first-level combine group
+constexpr uint32_t PERM_SENTINEL = 0xFFFFFFFFu;   // never a permutation entry: perm[i] < n <= 2^32 - 1
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -206,15 +209,11 @@ __host__ __device__ constexpr int jfast(uint32_t b) {
 
 template <int K>
 __device__ __forceinline__ void load_fixed_table(double *__restrict__ dst, const HaltonDev &h, const FusedConst<K> &fc) {
-    static_for<K>([&](auto Dc) {
-        constexpr int D = decltype(Dc)::value;
-        if constexpr (D >= 1) {
-            constexpr uint32_t b = prime_at(D);
-            constexpr int rows = ndmax32(b);
-            const uint32_t have = fc.ndc[D] * b;                // doubles the cached global table holds for this dimension
-            for (uint32_t e = threadIdx.x; e < rows * b; e += blockDim.x) dst[foff(D) + e] = e < have ? h.terms[fc.toff[D] + e] : 0.0;
-        }
-    });
+    // the host built the table in this very layout (host.cu: get_halton): one flat, coalesced copy (16 bytes per thread and trip)
+    (void)fc;
+    constexpr uint32_t N2 = (foff(K) + 1) / 2;
+    const double2 *src = reinterpret_cast<const double2 *>(h.fixed);
+    for (uint32_t e = threadIdx.x; e < N2; e += blockDim.x) reinterpret_cast<double2 *>(dst)[e] = src[e];
 }
 
 // One digit of (m -> m / b, term of m mod b) for two chains.  The in-order additions are __dadd_rn (no
@@ -422,7 +421,23 @@ __device__ __forceinline__ bool gen_rows_impl(const SourceDev &src, const FusedC
     uint64_t r = bt * 32 + lane;
     const bool valid = r < rows;
     const uint64_t i = i_begin + (valid ? r : rows - 1);
-    const uint64_t pi = src.perm[i];
+    uint64_t pi;
+    if (fc.poll_perm) {
+        // host permutation still on its way (one cudaMemcpyAsync enqueued before this launch): wait for my own entry
+        uint32_t v = 0u;
+        if (valid) {
+            uint32_t *pp = const_cast<uint32_t *>(src.perm) + i;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pp) : "memory");
+                if (v != PERM_SENTINEL) break;
+                __nanosleep(100);
+            }
+            *pp = PERM_SENTINEL;                          // leave the staging buffer clean for the next call
+        }
+        pi = v;
+    } else {
+        pi = src.perm[i];
+    }
     if (src.raw) {
         const double *ra = src.raw + i * (uint64_t)K, *rb = src.raw + (src.n + pi) * (uint64_t)K;
 #pragma unroll
@@ -629,7 +644,7 @@ fused_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_t i_
     extern __shared__ double smem[];
     double *terms = smem;                                           // shared copy of the Halton term table
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nterms = src.raw ? 0u : foff(K);
+    const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     volatile double *tokp = smem + nterms;                          // opaque functor token (see the functors)
     double *Y = smem + nterms + 1 + (size_t)warp * 32 * MP;         // this warp's [32][MP] value tile
     if (nterms) load_fixed_table<K>(terms, src.h, fc);
@@ -876,71 +891,116 @@ template <int K, int NB, int HB, bool PM>
 __host__ __device__ constexpr size_t wsd_tail_smem_doubles() {
     constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
-    return (size_t)128 + LROW + 2 * (size_t)(plen + 4) + rlen + 8;
+    return (size_t)128 + LROW + 2 * (size_t)(plen + 4) + rlen + 8;      // combine scratch | D | Pk | Pr | R
 }
 
-// Runs in the last CTA to finish (all threads).  smem: dynamic shared memory of the kernel, free for reuse.
+// Sum of `nrows` rows (LROW doubles each, row r at rows[r * LROW]) in row order into D (shared).  One double2 column (= one lane's
+// C fragment of one tile) per thread with 16 independent loads in flight; the four shifted sums by warp 0, lane l adding rows
+// l, l+32, ... in order and then the lanes in lane order.  Fixed order -> bit-reproducible.  All threads of the CTA call it.
+template <int NTL, int LROW>
+__device__ __forceinline__ void combine_rows(const double *__restrict__ rows, int nrows, double *__restrict__ D, double *__restrict__ ps) {
+    constexpr int L2 = LROW / 2;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const double2 *base = reinterpret_cast<const double2 *>(rows);
+    for (int c2 = tid; c2 < NTL * 32; c2 += nthr) {
+        const double2 *src = base + c2;
+        double2 acc = make_double2(0.0, 0.0);
+        int b = 0;
+        for (; b + 16 <= nrows; b += 16) {
+            double2 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+        }
+        for (; b + 4 <= nrows; b += 4) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+        }
+        for (; b < nrows; ++b) {
+            const double2 v = __ldcg(src + (size_t)b * L2);
+            acc.x += v.x; acc.y += v.y;
+        }
+        reinterpret_cast<double2 *>(D)[c2] = acc;
+    }
+    if (tid < 32) {
+        double2 s01 = make_double2(0.0, 0.0), s23 = make_double2(0.0, 0.0);
+        for (int b = tid; b < nrows; b += 32) {
+            const double2 v0 = __ldcg(base + (size_t)b * L2 + NTL * 32), v1 = __ldcg(base + (size_t)b * L2 + NTL * 32 + 1);
+            s01.x += v0.x; s01.y += v0.y; s23.x += v1.x; s23.y += v1.y;
+        }
+        double *lane4 = ps + tid * 4;
+        lane4[0] = s01.x; lane4[1] = s01.y; lane4[2] = s23.x; lane4[3] = s23.y;
+        __syncwarp();
+        if (tid < 8) {
+            double v = 0.0;
+            if (tid < 4)
+                for (int l = 0; l < 32; ++l) v += ps[l * 4 + tid];
+            D[NTL * 64 + tid] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// varsens/saltelli.py:577-622 for a scalar objective and compile-time K: finalize_body (device.cuh) with every index
+// computation folded at compile time (the generic form spends most of its ~6 us on run-time integer divisions).  Same
+// operations in the same order on the same operands, hence the same bits.  R = E_2 var_y U_j U_nj sens sens_t sens_2 sens_2n.
+template <int K>
+__device__ __forceinline__ void finalize_fixed(double n, double rows, const double *__restrict__ P, double *__restrict__ R) {
+    constexpr int m = 2 + 2 * K;
+    const double *G = P + 4;
+    auto at = [&](int p, int q) { return G[p * m - p * (p - 1) / 2 + (q - p)]; };           // p <= q
+    auto sym = [&](int p, int q) { return p <= q ? at(p, q) : at(q, p); };
+    const double e2 = at(0, 1) / n;                                                           // :577
+    const double tot = P[0] + P[1];
+    const double var = (P[2] + P[3] - tot * tot / (2.0 * rows)) / (2.0 * rows - 1.0);         // :583
+    double *Uj = R + 2, *Unj = Uj + K, *sens = Unj + K, *senst = sens + K, *s2 = senst + K, *s2n = s2 + K * K;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) { R[0] = e2; R[1] = var; }
+    for (int j = tid; j < K; j += nthr) {
+        const int iJ = 2 + j, iN = 2 + K + j;
+        double uj = at(0, iJ) / (n - 1.0);                                                    // :591-593
+        uj += at(1, iN) / (n - 1.0);
+        uj /= 2.0;
+        double unj = at(0, iN) / (n - 1.0);                                                   // :594-596
+        unj += at(1, iJ) / (n - 1.0);
+        unj /= 2.0;
+        Uj[j] = uj;
+        Unj[j] = unj;
+        sens[j] = (uj - e2) / var;                                                            // :608
+        senst[j] = 1.0 - ((unj - e2) / var);                                                  // :609
+    }
+    for (int e = tid; e < K * K; e += nthr) {
+        const int i = e / K, j = e - i * K;
+        const int Ji = 2 + i, Ni = 2 + K + i, Jj = 2 + j, Nj = 2 + K + j;
+        double v2 = at(Jj < Ni ? Jj : Ni, Jj < Ni ? Ni : Jj) + at(Ji < Nj ? Ji : Nj, Ji < Nj ? Nj : Ji);     // :612-613 (J < N always)
+        v2 /= 2.0 * (n - 1.0);
+        v2 -= e2;
+        v2 /= var;
+        double v2n = sym(Ni, Nj) + sym(Ji, Jj);                                               // :618-619
+        v2n /= 2.0 * (n - 1.0);
+        v2n -= e2;
+        v2n /= var;
+        s2[e] = v2;
+        s2n[e] = v2n;
+    }
+}
+
+// Runs in the CTA that completes the second-level combine (all threads).  On entry D (shared) holds the sums over all CTAs.
 template <int K, int NB, int HB, bool PM>
-__device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__restrict__ smem) {
+__device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__restrict__ smem, unsigned long long t0) {
     constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int NTL = wsd_ntl<NB, HB, PM>();
     constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
-    double *ps = smem;                                     // [128] scratch
-    double *D = ps + 128;                                  // [LROW]
+    double *D = smem + 128;                                // [LROW] (after the combine scratch)
     double *Pk = D + LROW;                                 // [plen] packed partial sums of this rank
     double *Pr = Pk + plen + 4;                            // [plen] reduced over ranks (mode 2)
     double *R = Pr + plen + 4;                             // [rlen] results
-    const int tid = threadIdx.x, nthr = blockDim.x, nb = gridDim.x;
-    const unsigned long long t0 = globaltimer_ns();
-    // 1. CTA rows -> D in CTA order.  One double2 column (= one lane's C fragment of one tile) per thread, 32 independent
-    //    loads in flight per thread: the 0.9 MB of CTA rows come through ONE SM, so memory-level parallelism is what counts
-    //    (8 ranges x 4 loads in flight took 18 us here; this form 3-4 us).  The four shifted sums are done by warp 0,
-    //    lane l adding CTAs l, l+32, ... in order, then the lanes in lane order.
-    {
-        constexpr int L2 = LROW / 2;
-        const double2 *base = reinterpret_cast<const double2 *>(tail.blockpart);
-        for (int c2 = tid; c2 < NTL * 32; c2 += nthr) {
-            const double2 *src = base + c2;
-            double2 acc = make_double2(0.0, 0.0);
-            int b = 0;
-            for (; b + 32 <= nb; b += 32) {
-                double2 v[32];
-#pragma unroll
-                for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
-#pragma unroll
-                for (int u = 0; u < 32; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
-            }
-            for (; b + 4 <= nb; b += 4) {
-                double2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
-            }
-            for (; b < nb; ++b) {
-                const double2 v = __ldcg(src + (size_t)b * L2);
-                acc.x += v.x; acc.y += v.y;
-            }
-            reinterpret_cast<double2 *>(D)[c2] = acc;
-        }
-        if (tid < 32) {
-            double2 s01 = make_double2(0.0, 0.0), s23 = make_double2(0.0, 0.0);
-            for (int b = tid; b < nb; b += 32) {
-                const double2 v0 = __ldcg(base + (size_t)b * L2 + NTL * 32), v1 = __ldcg(base + (size_t)b * L2 + NTL * 32 + 1);
-                s01.x += v0.x; s01.y += v0.y; s23.x += v1.x; s23.y += v1.y;
-            }
-            double *lane4 = ps + tid * 4;                   // ps: scratch
-            lane4[0] = s01.x; lane4[1] = s01.y; lane4[2] = s23.x; lane4[3] = s23.y;
-            __syncwarp();
-            if (tid < 4) {
-                double v = 0.0;
-                for (int l = 0; l < 32; ++l) v += ps[l * 4 + tid];
-                D[NTL * 64 + tid] = v;
-            }
-        }
-        __syncthreads();
-    }
-    // 2. packed partial-sum vector
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    // packed partial-sum vector
     for (int e = tid; e < plen; e += nthr) {
         const double v = e < 4 ? D[NTL * 64 + e] : packed_entry<K, NB, HB, PM>(D, e - 4);
         Pk[e] = v;
@@ -954,8 +1014,8 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     __shared__ unsigned timed_out;
     if (tid == 0) timed_out = 0u;
     if (tail.mode == 2) {
-        // 3. all-reduce over NVLink peer memory: my vector -> slot `rank` of every rank's buffer (one warp per peer, remote
-        //    stores), flag, wait for everybody's flag (bounded), sum the slots in rank order (same bits on every rank).
+        // all-reduce over NVLink peer memory: my vector -> slot `rank` of every rank's buffer (one warp per peer, remote
+        // stores), flag, wait for everybody's flag (bounded), sum the slots in rank order (same bits on every rank).
         const int set = (int)(tail.epoch & 1u), world = tail.world, rank = tail.rank;
         const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
         for (int r = warp; r < world; r += nwarp) {
@@ -971,7 +1031,7 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
             const unsigned *fl = reinterpret_cast<const unsigned *>(tail.peer_flags[rank]) + (size_t)set * world + tid;
             while (ld_acquire_sys_u32(fl) != tail.epoch) {
                 if (globaltimer_ns() - t2 > tail.timeout_ns) { timed_out = 1u; break; }
-                __nanosleep(64);
+                __nanosleep(32);
             }
         }
         __threadfence_system();
@@ -986,8 +1046,8 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
         __syncthreads();
         Pfin = Pr;
     }
-    // 4. estimators
-    finalize_body(K, 1, tail.n_total, tail.rows_total, Pfin, 1, R);
+    // estimators
+    finalize_fixed<K>(tail.n_total, tail.rows_total, Pfin, R);
     __syncthreads();
     for (int e = tid; e < rlen; e += nthr) {
         const double v = R[e];
@@ -997,12 +1057,11 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     if (tail.res_host && tid == 0) {
         double *x = tail.res_host + rlen;
         x[0] = timed_out ? 1.0 : 0.0;
-        x[1] = (double)(t1 - t0);                       // combine + pack, ns
+        x[1] = (double)(t1 - t0);                       // two-level combine (this CTA's share) + pack, ns
         x[2] = (double)(t2 - t1);                       // peer stores + fence + flags
         x[3] = (double)(t3 - t2);                       // wait for the peers
         x[4] = (double)(globaltimer_ns() - t3);         // rank-order sum + estimators + result stores
     }
-    __threadfence_system();
 }
 
 // Coordinate d (run-time: lane = coordinate, no divergence) of the Halton point m from the fixed-layout shared table; used
@@ -1054,7 +1113,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     __shared__ double shift_sh;
     __shared__ unsigned last_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nterms = src.raw ? 0u : foff(K);
+    const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     double *terms = smem;
     volatile double *tokp = smem + nterms;                                    // opaque functor token (see the functors)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + nterms + 1);        // full[WS_E][NBUF], empty[WS_E][NBUF]
@@ -1120,7 +1179,6 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         const uint64_t bars_total = 2 * count_of(0) + 1;              // count_of(0) is the largest batch count in the CTA
         uint64_t bars_done = 0;
         if (alternate && team == 1) { ebar(); ++bars_done; }
-        int chunk = 0;                                                // permutation chunks [0, chunk) are known to be in HBM
         for (uint64_t it = 0; it < cnt; ++it, bt += G) {
             const int slot = (int)(it % NBUF);
             double a[K], b[K];
@@ -1128,14 +1186,6 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
             const bool tr_on = fc.trace && blockIdx.x == 0 && lane == 0 && it < 64;
             long long *trp = fc.trace + ((size_t)warp * 64 + (it < 64 ? it : 0)) * 4;
             if (tr_on) trp[0] = clock64();
-            if (tail.arrive && (chunk == 0 || bt >= (uint64_t)tail.chunk_end_batch[chunk - 1])) {
-                // host permutation still on its way: wait (warp-uniform) until the slice that holds this batch has landed
-                int need = chunk;
-                while (need + 1 < tail.nchunk && bt >= (uint64_t)tail.chunk_end_batch[need]) ++need;
-                const unsigned long long want = tail.arrive_base + (unsigned long long)need + 1ull;
-                while (ld_acquire_sys_u64(tail.arrive) < want) __nanosleep(200);
-                chunk = need + 1;
-            }
             if (fc.debug & 1) {
 #pragma unroll
                 for (int d = 0; d < K; ++d) { a[d] = 0.25 + 1e-3 * lane + 1e-9 * (double)bt; b[d] = 0.75 - 1e-3 * lane; }
@@ -1231,22 +1281,50 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
             for (int w = 0; w < WS_E; ++w) v += sums[w * 4 + threadIdx.x];
         bp[NTL * 64 + threadIdx.x] = v;
     }
-    // ---- ticket: the last CTA to get here runs the tail (its result does not depend on WHICH CTA that is) ----
+    // ---- two-level ticket.  The last CTA of each group of TAIL_GROUP consecutive CTAs sums its group's rows (in CTA order); the
+    //      last group to finish sums the group rows (in group order) and runs the tail.  Which CTA does the work depends on
+    //      timing, what it computes does not.  One SM pulling all 148 rows (0.9 MB) through its L2 port took ~10 us; a group
+    //      of 16 rows plus 10 group rows take ~2. ----
+    const int group = blockIdx.x / TAIL_GROUP, ngroups = (gridDim.x + TAIL_GROUP - 1) / TAIL_GROUP;
+    const int gfirst = group * TAIL_GROUP;
+    const int gsize = (gfirst + TAIL_GROUP <= (int)gridDim.x) ? TAIL_GROUP : (int)gridDim.x - gfirst;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last_sh = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(tail.ticket + 1 + group, 1u);
+        last_sh = (t == (unsigned)gsize - 1u) ? 1u : 0u;
+        if (last_sh) tail.ticket[1 + group] = 0u;
+    }
     __syncthreads();
     if (!last_sh) return;
     __threadfence();
-    fused_tail<K, NB, HB, PM>(tail, smem);
-    if (threadIdx.x == 0) *tail.ticket = 0u;
+    const unsigned long long t0 = globaltimer_ns();
+    double *ps = smem, *D = smem + 128;
+    combine_rows<NTL, LROW>(tail.blockpart + (size_t)gfirst * LROW, gsize, D, ps);
+    if (ngroups > 1) {
+        double *gp = tail.grouppart + (size_t)group * LROW;
+        for (int e = threadIdx.x; e < LROW; e += blockDim.x) gp[e] = D[e];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(tail.ticket, 1u);
+            last_sh = (t == (unsigned)ngroups - 1u) ? 1u : 0u;
+            if (last_sh) tail.ticket[0] = 0u;
+        }
+        __syncthreads();
+        if (!last_sh) return;
+        __threadfence();
+        combine_rows<NTL, LROW>(tail.grouppart, ngroups, D, ps);
+    }
+    fused_tail<K, NB, HB, PM>(tail, smem, t0);
 }
 
-// f(M_1[0]): the common shift for the variance sums (identical on every rank).
+// f(M_1[0]): the common shift for the variance sums (identical on every rank) -- separate launch, used by the single-role
+// fused_kernel only (the warp-specialised kernel computes it in its prologue).
 template <int K, class F>
 __global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) {
     __shared__ double xs[K];
-    const int d = threadIdx.x;                     // one thread per coordinate: the table reads of the 20 chains overlap
+    const int d = threadIdx.x;                     // one thread per coordinate: the table reads of the K chains overlap
     if (d < K) {
         double p = src.raw ? src.raw[d] : halton_coord(src.h, d, (uint32_t)src.start);
         if (fc.scale_kind == VS_SCALE_LINEAR) p = __dadd_rn(__dmul_rn(p, fc.wr[d]), fc.lb[d]);
@@ -1285,7 +1363,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     constexpr int NTILES = SECOND ? NT * (NT + 1) / 2 : NT;
     constexpr int TPL = SECOND ? 1 : (NTILES + 31) / 32;
     constexpr int PER_BLOCK = TPL * 32 * T * T + 4;
-    const uint32_t nterms = src.raw ? 0u : foff(K);
+    const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
     const int variant = fused_variant_for<K>(c, SECOND);
@@ -1301,13 +1379,17 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             uint64_t wantd = (nbatch + eps * WS_S - 1) / (eps * WS_S);
             int gridd = (int)(wantd < (uint64_t)c->sm_count ? wantd : (uint64_t)c->sm_count);
             if (gridd < 1) gridd = 1;
-            VS_TRY(ensure(c, c->block_buf, (size_t)gridd * LROWk * sizeof(double)));
+            const int ngroups = (gridd + TAIL_GROUP - 1) / TAIL_GROUP;
+            VS_REQUIRE(ngroups < 60, VS_ERR_UNSUPPORTED, "grid of %d CTAs needs more ticket counters than the ctx holds", gridd);
+            VS_TRY(ensure(c, c->block_buf, (size_t)(gridd + ngroups) * LROWk * sizeof(double)));
             if (!c->ticket_buf.p) {
                 VS_TRY(ensure(c, c->ticket_buf, 256));
                 VS_CUDA(cudaMemsetAsync(c->ticket_buf.p, 0, 256, c->stream));
             }
             FusedTail tail{};
             tail.blockpart = (double *)c->block_buf.p;
+            tail.grouppart = (double *)c->block_buf.p + (size_t)gridd * LROWk;
+            tail.poll_perm = (req && req->poll_perm) ? 1 : 0;
             tail.ticket = (unsigned *)c->ticket_buf.p;
             tail.partials = partials;
             tail.mode = req ? req->mode : 0;
@@ -1324,12 +1406,6 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
                 tail.peer_bufs = req->peer_bufs_dev;
                 tail.peer_flags = req->peer_flags_dev;
                 tail.timeout_ns = (unsigned long long)c->opt.p2p_timeout_ms * 1000000ull;
-            }
-            if (req && req->arrive_dev) {
-                tail.arrive = req->arrive_dev;
-                tail.arrive_base = req->arrive_base;
-                tail.nchunk = req->nchunk;
-                for (int ch = 0; ch < 16; ++ch) tail.chunk_end_batch[ch] = req->chunk_end_batch[ch];
             }
             size_t smem_run = ((size_t)nterms + 1 + 2 * eps * WS_S + (size_t)eps * WS_S * MPADk * YT_PITCH) * sizeof(double);
             size_t smem_red = ((size_t)WS_S * NTLk * 64 + 4 * eps * WS_S) * sizeof(double);
@@ -1353,7 +1429,9 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
                 if (c->device < 64) smem_set[c->device][ki] = smem;
             }
             time_begin(c);
-            kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fc, f, i_begin, i_end, tail);
+            FusedConst<K> fcl = fc;
+            fcl.poll_perm = tail.poll_perm;
+            kern<<<gridd, (eps + 1) * WS_S * 32, smem, c->stream>>>(src, fcl, f, i_begin, i_end, tail);
             time_end(c);
             c->launches++;
             VS_CUDA(cudaGetLastError());
@@ -1375,7 +1453,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
         }
     }
     VS_REQUIRE(partials, VS_ERR_ARG, "this fused kernel variant needs a partial-sum buffer");
-    VS_REQUIRE(!(req && req->arrive_dev), VS_ERR_UNSUPPORTED, "this fused kernel variant cannot poll permutation chunks");
+    VS_REQUIRE(!(req && req->poll_perm), VS_ERR_UNSUPPORTED, "this fused kernel variant cannot poll a permutation in flight");
     const int ewarps = FUSED_WARPS;
     uint64_t want = (nbatch + ewarps - 1) / ewarps;
     int grid = (int)(want < (uint64_t)c->sm_count ? want : (uint64_t)c->sm_count);
@@ -1418,6 +1496,7 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
         fc.ndc[d] = 0;
     }
     fc.small_index = 0;
+    fc.poll_perm = 0;
     fc.trace = nullptr;
     fc.alternate = c->opt.alternate;
     for (int u = 0; u < FusedConst<K>::AR_N; ++u)
@@ -1449,6 +1528,8 @@ static int fill_const(vs_ctx *c, const SourceDev &src, const ScaleDev &s, FusedC
                 }
         }
         VS_REQUIRE(off == src.h.total_terms, VS_ERR_ARG, "Halton table layout mismatch (%u vs %u)", off, src.h.total_terms);
+        VS_REQUIRE(src.h.fixed && src.h.fixed_len >= foff(K), VS_ERR_ARG, "fixed-layout Halton table missing (%u of %u doubles)",
+                   src.h.fixed_len, (uint32_t)foff(K));
     }
     return VS_OK;
 }

@@ -100,11 +100,11 @@ bool capturing(vs_ctx *c) {
     return st != cudaStreamCaptureStatusNone;
 }
 void time_begin(vs_ctx *c) {
-    if (capturing(c)) return;                     // events recorded inside a CUDA graph capture cannot be timed
+    if (!c->timing || capturing(c)) return;       // events recorded inside a CUDA graph capture cannot be timed
     cudaEventRecord(c->ev0, c->stream);
 }
 void time_end(vs_ctx *c) {
-    if (capturing(c)) return;
+    if (!c->timing || capturing(c)) return;
     cudaEventRecord(c->ev1, c->stream);
     c->timed = true;
 }
@@ -214,8 +214,20 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         build_terms(bases, nd, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, off, terms);
         std::vector<uint64_t> magic(k);
         for (int d = 0; d < k; ++d) magic[d] = (~0ull) / bases[d] + 1ull;   // floor((2^64-1)/b)+1 == floor(2^64/b)+1 for b not a power of 2; b=2 unused
+        // The fused kernels keep the table in shared memory in a FIXED layout (fused_impl.cuh: foff / ndmax32): dimension d >= 1
+        // owns ndmax32(b_d) rows -- every digit position a 32-bit index can have -- so that row addresses are compile-time
+        // constants; it is built here once and copied by every CTA with one flat, coalesced loop.
+        std::vector<double> fixed;
+        if (k <= 32) {
+            std::vector<uint32_t> nd32, off32;
+            digit_counts(bases, 0xFFFFFFFFull, nd32);
+            std::vector<uint32_t> b1(bases.begin() + 1, bases.end()), n1(nd32.begin() + 1, nd32.end());
+            build_terms(b1, n1, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, off32, fixed);
+        }
         size_t nb_terms = terms.size() * sizeof(double), nb_magic = (size_t)k * 8, nb_u32 = (size_t)k * 4;
-        size_t total = nb_terms + nb_magic + 2 * nb_u32 + 64;
+        size_t nb_fixed = ((fixed.size() + 1) & ~(size_t)1) * sizeof(double);
+        nb_terms = (nb_terms + 15) & ~(size_t)15;
+        size_t total = nb_terms + nb_fixed + nb_magic + 2 * nb_u32 + 64;
         if (hc.blob) {
             VS_CUDA(cudaStreamSynchronize(c->stream));
             VS_CUDA(cudaFree(hc.blob));
@@ -223,9 +235,13 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         }
         VS_CUDA(cudaMalloc(&hc.blob, total));
         char *p = (char *)hc.blob;
-        VS_CUDA(cudaMemcpy(p, terms.data(), nb_terms, cudaMemcpyHostToDevice));
+        VS_CUDA(cudaMemcpy(p, terms.data(), terms.size() * sizeof(double), cudaMemcpyHostToDevice));
         hc.dev.terms = (const double *)p;
         p += nb_terms;
+        if (!fixed.empty()) VS_CUDA(cudaMemcpy(p, fixed.data(), fixed.size() * sizeof(double), cudaMemcpyHostToDevice));
+        hc.dev.fixed = fixed.empty() ? nullptr : (const double *)p;
+        hc.dev.fixed_len = (uint32_t)fixed.size();
+        p += nb_fixed;
         VS_CUDA(cudaMemcpy(p, magic.data(), nb_magic, cudaMemcpyHostToDevice));
         hc.dev.magic = (const uint64_t *)p;
         p += nb_magic;
@@ -376,7 +392,6 @@ extern "C" int vs_ctx_create(int device, vs_ctx **out) {
     c->stream = c->own_stream;
     VS_CUDA(cudaEventCreate(&c->ev0));
     VS_CUDA(cudaEventCreate(&c->ev1));
-    VS_CUDA(cudaHostAlloc((void **)&c->host_seq, 64 * sizeof(unsigned long long), cudaHostAllocPortable));
     load_options(c->opt);
     *out = c;
     return VS_OK;
@@ -388,8 +403,7 @@ extern "C" int vs_ctx_destroy(vs_ctx *c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
     if (c->host_res) cudaFreeHost(c->host_res);
-    if (c->host_seq) cudaFreeHost(c->host_seq);
-    DevBuf *bufs[] = {&c->ticket_buf, &c->peer_buf, &c->pipe_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
+    DevBuf *bufs[] = {&c->poll_buf, &c->ticket_buf, &c->peer_buf, &c->pipe_buf, &c->scale_buf, &c->obj_buf, &c->perm_buf, &c->raw_buf, &c->io_buf,
                       &c->part_buf,  &c->block_buf, &c->res_buf, &c->dir_buf, &c->misc_buf};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -411,6 +425,13 @@ extern "C" int vs_ctx_set_stream(vs_ctx *c, void *stream) {
     return VS_OK;
 }
 
+extern "C" int vs_ctx_set_timing(vs_ctx *c, int on) {
+    VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
+    c->timing = on != 0;
+    if (!c->timing) c->timed = false;
+    return VS_OK;
+}
+
 extern "C" int vs_ctx_reload_env(vs_ctx *c) {
     VS_REQUIRE(c, VS_ERR_ARG, "ctx is NULL");
     load_options(c->opt);
@@ -428,7 +449,7 @@ extern "C" uint64_t vs_ctx_launch_count(const vs_ctx *c) { return c ? c->launche
 
 extern "C" int vs_last_kernel_ms(vs_ctx *c, float *ms) {
     VS_REQUIRE(c && ms, VS_ERR_ARG, "NULL argument");
-    VS_REQUIRE(c->timed, VS_ERR_ARG, "no timed kernel has run on this ctx");
+    VS_REQUIRE(c->timed, VS_ERR_ARG, "no timed kernel has run on this ctx (enable timing with vs_ctx_set_timing)");
     VS_CUDA(cudaSetDevice(c->device));
     VS_CUDA(cudaEventSynchronize(c->ev1));
     VS_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));

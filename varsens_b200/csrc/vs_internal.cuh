@@ -50,6 +50,8 @@ struct HaltonDev {
     const uint32_t *off;
     uint32_t total_terms;
     int mode;               // enum vs_halton_mode (HORNER: the table is not used)
+    const double *fixed;    // the same terms in the fused kernels' fixed layout (all digit positions of a 32-bit index), k <= 32
+    uint32_t fixed_len;
 };
 
 // scale.py:33 / :62 lowered: linear  -> p * w + lb   (w = ub - lb rounded on the host, as numpy does)
@@ -129,11 +131,7 @@ struct FusedReq {
     int world = 1, rank = 0;
     uint32_t epoch = 0;
     const uint64_t *peer_bufs_dev = nullptr, *peer_flags_dev = nullptr;
-    // arrival of the permutation slices of a host permutation (chunk c is complete when *arrive_dev >= arrive_base + c + 1)
-    const unsigned long long *arrive_dev = nullptr;
-    unsigned long long arrive_base = 0;
-    int nchunk = 0;
-    uint32_t chunk_end_batch[16] = {0};
+    int poll_perm = 0;                  // the permutation is copied into its staging buffer while the kernel runs (sentinel polling)
 };
 
 }  // namespace vs
@@ -144,6 +142,7 @@ struct vs_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D staging overlapped with compute
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;                 // record events around the main kernel of each call (vs_ctx_set_timing)
     bool timed = false;
     uint64_t launches = 0;
     int sm_count = 0;
@@ -156,12 +155,12 @@ struct vs_ctx {
     vs::Options opt;
     double *host_res = nullptr;          // mapped pinned host memory the fused kernel's tail writes the results to
     size_t host_res_cap = 0;             // doubles
-    unsigned long long *host_seq = nullptr;   // pinned ring of sequence numbers (sources of the chunk-arrival flag copies)
-    unsigned long long seq = 0;          // last sequence number handed out
-    vs::DevBuf ticket_buf;               // ticket counter of the fused kernel's last-CTA tail + chunk-arrival flag
+    vs::DevBuf ticket_buf;               // ticket counters of the fused kernel's two-level combine (64 x uint32, zero between launches)
+    vs::DevBuf poll_buf;                 // staging buffer of a host permutation that is polled while it arrives: all entries hold the
+    bool poll_clean = false;             // sentinel 0xFFFFFFFF between calls (the kernel puts it back); false -> refill before use
     int scale_kind_cached = -1, scale_k_cached = -1, obj_id_cached = -1;
     // scratch
-    std::vector<cudaEvent_t> pipe_ev;    // chunk-arrival events of the pipelined host-permutation path
+    std::vector<cudaEvent_t> pipe_ev;    // [0]: "compute stream is done with the staging buffer" (ordering of the next H2D copy)
     vs::DevBuf pipe_buf;
     vs::DevBuf scale_buf, obj_buf, perm_buf, raw_buf, io_buf, part_buf, block_buf, res_buf, dir_buf, misc_buf;
 };

@@ -156,8 +156,7 @@ def fused_step(ctx, k, n, perm, objective, params, discard, scale, raw, flags):
     plen = partials_layout(k)["length"]
     ex = None if use_nccl() else peer_exchange(plen, device)
     if ex is not None and hi > lo:
-        return ctx.run_fused_p2p(k, n, perm, objective, params, ex.world, ex.rank, ex.peer_bufs, ex.peer_flags, ex.next_epoch(),
-                                 lo, hi, discard, scale, raw, flags)
+        return ctx.fused_plan(k, n, perm, objective, params, discard, scale, raw, flags, lo, hi, ex).run()
     part = torch.empty(plen, dtype=torch.float64, device=device)
     with on_torch_stream(ctx, device):
         ctx.fused_partials(k, n, perm, objective, params, discard, scale, raw, lo, hi, flags, out=part)
