@@ -229,9 +229,11 @@ int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops);
 int vs_ctx_set_timing(vs_ctx *ctx, int on);
 int vs_last_kernel_ms(vs_ctx *ctx, float *ms);
 /* Time stamps (ns, %globaltimer) of the tail of the last one-launch fused step with estimators (vs_run_fused /
- * vs_run_fused_p2p, k factors): ns4 = {combine + pack, peer stores + fence + flags, wait for the peers, rank-order sum +
- * estimators + result stores}. */
-int vs_last_tail_ns(vs_ctx *ctx, int k, double *ns4);
+ * vs_run_fused_p2p, k factors), taken in the CTA that finished last: ns8 = {combine + pack (total), peer stores + fence +
+ * flags, wait for the peers, rank-order sum + estimators + result stores; then the parts of the first: first-level combine,
+ * group row + fence + ticket, second-level combine, packing; then that CTA's own prologue, main loop and CTA-level combine}
+ * -- 11 doubles. */
+int vs_last_tail_ns(vs_ctx *ctx, int k, double *ns11);
 
 #ifdef __cplusplus
 }

@@ -275,7 +275,7 @@ class Context(object):
 
     def last_tail_ns(self, k):
         """ns spent in {combine+pack, peer stores, wait for peers, sum+estimators} by the tail of the last fused step."""
-        a = numpy.zeros(4)
+        a = numpy.zeros(11)
         check(lib().vs_last_tail_ns(self._h, int(k), a.ctypes.data_as(ctypes.c_void_p)))
         return a
 

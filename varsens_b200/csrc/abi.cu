@@ -413,10 +413,10 @@ extern "C" int vs_run_fused_p2p(vs_ctx *c, int k, uint64_t n, uint64_t discard, 
     return VS_OK;
 }
 
-extern "C" int vs_last_tail_ns(vs_ctx *c, int k, double *ns4) {
-    VS_REQUIRE(c && ns4 && c->host_res, VS_ERR_ARG, "no fused step has run on this ctx");
+extern "C" int vs_last_tail_ns(vs_ctx *c, int k, double *ns8) {
+    VS_REQUIRE(c && ns8 && c->host_res, VS_ERR_ARG, "no fused step has run on this ctx");
     const double *x = c->host_res + result_len(k, 1);
-    for (int i = 0; i < 4; ++i) ns4[i] = x[1 + i];
+    for (int i = 0; i < 11; ++i) ns8[i] = x[1 + i];
     return VS_OK;
 }
 

@@ -905,24 +905,12 @@ __device__ __forceinline__ void combine_rows(const double *__restrict__ rows, in
     for (int c2 = tid; c2 < NTL * 32; c2 += nthr) {
         const double2 *src = base + c2;
         double2 acc = make_double2(0.0, 0.0);
-        int b = 0;
-        for (; b + 16 <= nrows; b += 16) {
+        for (int b = 0; b < nrows; b += 16) {           // 16 independent loads in flight, predicated (a short tail is one round trip too)
             double2 v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
+            for (int u = 0; u < 16; ++u) v[u] = (b + u < nrows) ? __ldcg(src + (size_t)(b + u) * L2) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
-        }
-        for (; b + 4 <= nrows; b += 4) {
-            double2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(b + u) * L2);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
-        }
-        for (; b < nrows; ++b) {
-            const double2 v = __ldcg(src + (size_t)b * L2);
-            acc.x += v.x; acc.y += v.y;
         }
         reinterpret_cast<double2 *>(D)[c2] = acc;
     }
@@ -991,7 +979,8 @@ __device__ __forceinline__ void finalize_fixed(double n, double rows, const doub
 
 // Runs in the CTA that completes the second-level combine (all threads).  On entry D (shared) holds the sums over all CTAs.
 template <int K, int NB, int HB, bool PM>
-__device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__restrict__ smem, unsigned long long t0) {
+__device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__restrict__ smem, unsigned long long t0, unsigned long long ta,
+                                           unsigned long long tb, unsigned long long tc) {
     constexpr int LROW = wsd_lrow<NB, HB, PM>();
     constexpr int NTL = wsd_ntl<NB, HB, PM>();
     constexpr int m = 2 + 2 * K, plen = 4 + m * (m + 1) / 2, rlen = 2 + 4 * K + 2 * K * K;
@@ -1061,6 +1050,10 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
         x[2] = (double)(t2 - t1);                       // peer stores + fence + flags
         x[3] = (double)(t3 - t2);                       // wait for the peers
         x[4] = (double)(globaltimer_ns() - t3);         // rank-order sum + estimators + result stores
+        x[5] = (double)(ta - t0);                       // first-level combine (my group's rows)
+        x[6] = (double)(tb - ta);                       // group row to HBM + fence + second-level ticket
+        x[7] = (double)(tc - tb);                       // second-level combine
+        x[8] = (double)(t1 - tc);                       // packed partial-sum vector
     }
 }
 
@@ -1112,6 +1105,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     __shared__ double xs_sh[K];
     __shared__ double shift_sh;
     __shared__ unsigned last_sh;
+    const unsigned long long t_entry = globaltimer_ns();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     double *terms = smem;
@@ -1143,6 +1137,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     __syncthreads();
     auto full_bar = [&](int e, int slot) { return bars + (e * NBUF + slot); };
     auto empty_bar = [&](int e, int slot) { return bars + NBUF * WS_E + (e * NBUF + slot); };
+    const unsigned long long t_pro = globaltimer_ns();
 
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
@@ -1254,6 +1249,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
 
     // ---- combine: every S-warp drops its C fragments into a compact tile-major image, summed in S-warp order ----
     __syncthreads();
+    const unsigned long long t_loop = globaltimer_ns();
     double *img = smem;                                   // [WS_S][NTL*64] then [WS_E][4]
     double *sums = img + (size_t)WS_S * NTL * 64;
     if (warp < WS_S) {
@@ -1301,6 +1297,8 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     const unsigned long long t0 = globaltimer_ns();
     double *ps = smem, *D = smem + 128;
     combine_rows<NTL, LROW>(tail.blockpart + (size_t)gfirst * LROW, gsize, D, ps);
+    const unsigned long long ta = globaltimer_ns();
+    unsigned long long tb = ta, tc = ta;
     if (ngroups > 1) {
         double *gp = tail.grouppart + (size_t)group * LROW;
         for (int e = threadIdx.x; e < LROW; e += blockDim.x) gp[e] = D[e];
@@ -1314,9 +1312,17 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         __syncthreads();
         if (!last_sh) return;
         __threadfence();
+        tb = globaltimer_ns();
         combine_rows<NTL, LROW>(tail.grouppart, ngroups, D, ps);
+        tc = globaltimer_ns();
     }
-    fused_tail<K, NB, HB, PM>(tail, smem, t0);
+    fused_tail<K, NB, HB, PM>(tail, smem, t0, ta, tb, tc);
+    if (tail.mode >= 1 && tail.res_host && threadIdx.x == 0) {      // this CTA's own phases (diagnostics)
+        double *x = tail.res_host + (2 + 4 * K + 2 * K * K);
+        x[9] = (double)(t_pro - t_entry);                            // prologue: table copy, tile zeroing, barriers, shift
+        x[10] = (double)(t_loop - t_pro);                            // main loop
+        x[11] = (double)(t0 - t_loop);                               // CTA combine + row to HBM + fence + first-level ticket
+    }
 }
 
 // f(M_1[0]): the common shift for the variance sums (identical on every rank) -- separate launch, used by the single-role
