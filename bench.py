@@ -341,8 +341,10 @@ def run_gpu(args, rank, world):
                    "l2": "192 MiB buffer written between timed iterations (L2 flush)",
                    "step": "ONE kernel launch per rank: generation + evaluation + Gram + fixed-order combine%s + estimators, results written to mapped host memory" % (" + peer-memory all-reduce" if ex is not None else "") if (world == 1 or ex is not None) else "vs_fused_partials (1 launch) + NCCL all_reduce + finalize kernel"},
         "index_time": {"partials_to_host_indices_ms": index_ms, "what": "%sfinalize kernel writing to mapped host memory, timed alone" % ("NCCL all-reduce of the partial sums + " if world > 1 else ""),
-                       "in_kernel_tail_ns": {"combine_pack": tail_ns[0], "peer_stores_flags": tail_ns[1], "wait_for_peers": tail_ns[2], "sum_estimators_store": tail_ns[3],
-                                             "what": "globaltimer stamps inside the last CTA of the fused kernel, last resident step, rank 0"},
+                       "in_kernel_tail_ns": {"combine_pack": tail_ns[0], "peer_stores": tail_ns[1], "wait_and_sum_peers": tail_ns[2], "estimators_store": tail_ns[3],
+                                             "first_level_combine": tail_ns[4], "group_row_fence_ticket": tail_ns[5], "second_level_combine": tail_ns[6], "pack": tail_ns[7],
+                                             "cta_prologue": tail_ns[8], "cta_main_loop": tail_ns[9], "cta_combine_ticket": tail_ns[10],
+                                             "what": "globaltimer stamps inside the CTA that finished last, last resident step, rank 0"},
                        "values_to_host_indices_ms": index_values_ms, "values_what": "vs_indices_from_values on 2n(1+k) = %d resident values (bulk-copy + DMMA Gram kernel)" % evals(n)},
         "e2e": {"value": evals(n) / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(4 * (hi - lo) * world), "d2h_bytes_per_step": int(8 * (2 + 4 * k + 2 * k * k)),

@@ -179,12 +179,13 @@ int vs_finalize(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const doub
 int vs_finalize_device(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, const double *partials_dev, int flags,
                        double *result_dev);
 /* Multi-GPU: vs_finalize fused with the all-reduce, over NVLink peer memory (no NCCL call).  ONE single-CTA kernel per
- * rank: stores this rank's partial sums into slot `rank` of every peer's exchange buffer (peer_bufs[r], device pointers
- * mapped into this process, e.g. torch symmetric memory), publishes an epoch flag to every peer (peer_flags[r][rank]),
- * waits for the world_size flags in its own flag array, sums the slots in rank order (identical bits on every rank) and
- * computes the indices.  Each peer buffer holds 2 * world_size * vs_partials_len(k,l) doubles and each flag array
- * 2 * world_size uint32 (double-buffered on the epoch parity; zero-initialised).  epoch must start at 1 and increase by one
- * per call on every rank.  Replaces the file-batch gather of varsens/saltelli.py:415-472 + :572-622. */
+ * rank, low-latency protocol: every double of this rank's partial sums is stored as one 16-byte unit {lo, epoch, hi, epoch}
+ * into slot `rank` of every peer's exchange buffer (peer_bufs[r], device pointers mapped into this process, e.g. torch
+ * symmetric memory; one warp per peer); each rank then polls the tags of its own buffer -- at most VS_P2P_TIMEOUT_MS, then
+ * VS_ERR_TIMEOUT --, sums the world_size slots in rank order (identical bits on every rank) and computes the indices.  No
+ * fence, no separate flag.  Each peer buffer holds 2 (epoch parity) * world_size * vs_partials_len(k,l) * 16 bytes,
+ * zero-initialised; epoch must start at 1 and increase by one per call on every rank.  peer_flags is ignored (kept in the
+ * signature for ABI stability; may be NULL).  Replaces the file-batch gather of varsens/saltelli.py:415-472 + :572-622. */
 int vs_allreduce_finalize_p2p(vs_ctx *ctx, int k, int l, uint64_t n, uint64_t rows, int world_size, int rank,
                               const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch,
                               const double *partials_dev, int flags, vs_result *result);
@@ -210,9 +211,9 @@ int vs_run_fused(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_
 
 /* Multi-GPU form of vs_run_fused: ONE kernel launch per rank and step.  Rank `rank` of `world_size` evaluates base rows
  * [i_begin,i_end) of the n-row design; the last CTA of its kernel combines the CTA sums in fixed order, stores the packed
- * partial sums into slot `rank` of every peer's exchange buffer over NVLink (one warp per peer), publishes the epoch flag,
- * waits -- at most VS_P2P_TIMEOUT_MS (default 10 s), then VS_ERR_TIMEOUT -- for the other ranks, sums the slots in rank
- * order (identical bits on every rank), computes the estimators and writes them to mapped host memory.  Buffers, flags and
+ * partial sums into slot `rank` of every peer's exchange buffer over NVLink (one warp per peer, 16-byte {lo, epoch, hi, epoch}
+ * units), polls -- at most VS_P2P_TIMEOUT_MS (default 10 s), then VS_ERR_TIMEOUT -- the tags of its own buffer, sums the slots
+ * in rank order (identical bits on every rank), computes the estimators and writes them to mapped host memory.  Buffers and
  * epoch are those of vs_allreduce_finalize_p2p.  There is no NCCL call and no separate reduction, finalisation or copy
  * launch.  Replaces varsens/saltelli.py:82-125, :308-353, :572-622 and the file-batch gather of :415-472. */
 int vs_run_fused_p2p(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
@@ -229,8 +230,8 @@ int vs_measure_fp64_peak(vs_ctx *ctx, double *tflops);
 int vs_ctx_set_timing(vs_ctx *ctx, int on);
 int vs_last_kernel_ms(vs_ctx *ctx, float *ms);
 /* Time stamps (ns, %globaltimer) of the tail of the last one-launch fused step with estimators (vs_run_fused /
- * vs_run_fused_p2p, k factors), taken in the CTA that finished last: ns8 = {combine + pack (total), peer stores + fence +
- * flags, wait for the peers, rank-order sum + estimators + result stores; then the parts of the first: first-level combine,
+ * vs_run_fused_p2p, k factors), taken in the CTA that finished last: {combine + pack (total), peer stores, wait for the
+ * peers' elements + rank-order sum, estimators + result stores; then the parts of the first: first-level combine,
  * group row + fence + ticket, second-level combine, packing; then that CTA's own prologue, main loop and CTA-level combine}
  * -- 11 doubles. */
 int vs_last_tail_ns(vs_ctx *ctx, int k, double *ns11);

@@ -207,13 +207,13 @@ extern "C" int vs_allreduce_finalize_p2p(vs_ctx *c, int k, int l, uint64_t n, ui
                                          const double *partials_dev, int flags, vs_result *result) {
     VS_TRY(check_common(c, k));
     VS_REQUIRE(l >= 1 && l <= 64 && n >= 2 && rows >= 1 && rows <= n && partials_dev && result, VS_ERR_ARG, "bad arguments");
-    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && peer_flags && epoch >= 1,
+    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && epoch >= 1,
                VS_ERR_ARG, "bad peer description");
     // the two pointer tables travel as kernel-visible device arrays (dir_buf: world_size * 2 pointers)
     VS_TRY(ensure(c, c->peer_buf, 2 * 64 * sizeof(uint64_t)));
     uint64_t *tab = (uint64_t *)c->peer_buf.p;
     std::vector<uint64_t> want(128, 0);
-    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags[r]; }
+    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags ? peer_flags[r] : 0; }
     if (want != c->peer_tab) {                              // uploaded once per exchange, not per call
         c->peer_tab = want;
         VS_CUDA(cudaMemcpyAsync(tab, c->peer_tab.data(), 128 * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
@@ -377,12 +377,12 @@ extern "C" int vs_run_fused_p2p(vs_ctx *c, int k, uint64_t n, uint64_t discard, 
                                 const uint64_t *peer_bufs, const uint64_t *peer_flags, uint32_t epoch, vs_result *result) {
     VS_TRY(check_common(c, k));
     VS_REQUIRE(n >= 2 && i_begin < i_end && i_end <= n && result, VS_ERR_ARG, "bad arguments (every rank needs at least one base row)");
-    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && peer_flags && epoch >= 1,
+    VS_REQUIRE(world_size >= 1 && world_size <= 64 && rank >= 0 && rank < world_size && peer_bufs && epoch >= 1,
                VS_ERR_ARG, "bad peer description");
     VS_TRY(ensure(c, c->peer_buf, 2 * 64 * sizeof(uint64_t)));
     uint64_t *tab = (uint64_t *)c->peer_buf.p;
     std::vector<uint64_t> want(128, 0);
-    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags[r]; }
+    for (int r = 0; r < world_size; ++r) { want[r] = peer_bufs[r]; want[64 + r] = peer_flags ? peer_flags[r] : 0; }
     if (want != c->peer_tab) {                              // uploaded once per exchange, not per call
         VS_CUDA(cudaStreamSynchronize(c->stream));
         c->peer_tab = want;

@@ -257,6 +257,58 @@ __device__ __forceinline__ void finalize_body(int k, int l, double n, double row
 }
 
 // ---------------------------------------------------------------------------------------------
+// All-reduce of the partial-sum vector over NVLink peer memory, low-latency protocol: no fence, no separate flag.
+// Every double travels as ONE 16-byte store {lo, epoch, hi, epoch}: each 8-byte half carries its own tag and is written
+// atomically, so a reader that sees both tags equal to the current epoch has the value (what NCCL's LL protocol relies on).
+// Rank r's vector goes to slot r of every rank's buffer (set = epoch parity: a rank that is one step ahead cannot overwrite
+// slots somebody is still reading); every rank sums the world slots in rank order -> identical bits everywhere.
+// Exchange buffer of a rank: 2 sets x world slots x plen elements x 16 bytes, zero-initialised; epoch starts at 1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(void *dst, double v, unsigned epoch) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
+}
+// one warp per peer: src[0..plen) -> slot `rank` of every peer's set
+__device__ __forceinline__ void ll_push(const uint64_t *__restrict__ bufs, int world, int rank, unsigned epoch, int plen,
+                                        const double *__restrict__ src) {
+    const int set = (int)(epoch & 1u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int r = warp; r < world; r += nwarp) {
+        char *dst = reinterpret_cast<char *>(bufs[r]) + (((size_t)set * world + rank) * plen) * 16;
+        for (int e = lane; e < plen; e += 32) ll_store(dst + (size_t)e * 16, src[e], epoch);
+    }
+}
+// dst[e] = sum over ranks (rank order) of slot r element e of MY buffer; waits (bounded) for each element's tags.
+// Returns false if some element did not arrive within timeout_ns (dst is then incomplete).
+__device__ __forceinline__ bool ll_reduce(const uint64_t *__restrict__ bufs, int world, int rank, unsigned epoch, int plen,
+                                          double *__restrict__ dst, unsigned long long timeout_ns) {
+    const int set = (int)(epoch & 1u);
+    const char *mine = reinterpret_cast<const char *>(bufs[rank]) + ((size_t)set * world * plen) * 16;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    bool ok = true;
+    for (int e = threadIdx.x; e < plen; e += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const char *p = mine + ((size_t)r * plen + e) * 16;
+            unsigned lo, f0, hi, f1;
+            for (;;) {
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+                if (f0 == epoch && f1 == epoch) break;
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) { ok = false; break; }
+            }
+            if (!ok) break;
+            s += __hiloint2double((int)hi, (int)lo);
+        }
+        dst[e] = s;
+        if (!ok) break;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

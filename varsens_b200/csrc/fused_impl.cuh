@@ -857,17 +857,13 @@ __device__ __forceinline__ double dense_at(const double *__restrict__ D, int x, 
     return D[t * 64 + (lo & 7) * 8 + (hi & 7)];
 }
 
-// Entry e of the packed upper triangle of G (v = (A, B, J_0.., N_0..), include/varsens_b200.h) from the combined CTA sums.
+// Entry (p, q), p <= q, of the packed upper triangle of G (v = (A, B, J_0.., N_0..), include/varsens_b200.h) from the combined CTA sums.
 // Paired layout (Grams of w = (P, A, B) and u = (M, A, B), HS coordinates each): first-order entries are exact recombinations
 // (A.J_j = (A.P_j - A.M_j)/2, A.N_j = (A.P_j + A.M_j)/2); the J/N blocks come out symmetrised,
 //   G[J_i][J_j] = G[N_i][N_j] = (N_i.N_j + J_i.J_j)/2,   G[J_i][N_j] = (N_i.J_j + J_i.N_j)/2,
 // which is all the estimators read (they add the two members of each pair, saltelli.py:612-613,618-619).
 template <int K, int NB, int HB, bool PM>
-__device__ __forceinline__ double packed_entry(const double *__restrict__ D, int e) {
-    constexpr int m = 2 + 2 * K;
-    int p = 0, rowlen = m, rem = e;
-    while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
-    const int q = p + rem;
+__device__ __forceinline__ double packed_pq(const double *__restrict__ D, int p, int q) {      // p <= q
     if constexpr (!PM) {
         return dense_at<NB, HB, PM>(D, p, q);
     } else {
@@ -989,11 +985,18 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     double *Pr = Pk + plen + 4;                            // [plen] reduced over ranks (mode 2)
     double *R = Pr + plen + 4;                             // [rlen] results
     const int tid = threadIdx.x, nthr = blockDim.x;
-    // packed partial-sum vector
-    for (int e = tid; e < plen; e += nthr) {
-        const double v = e < 4 ? D[NTL * 64 + e] : packed_entry<K, NB, HB, PM>(D, e - 4);
-        Pk[e] = v;
-        if (tail.partials) tail.partials[e] = v;
+    // packed partial-sum vector: warp w takes rows p = w, w + nwarp, ... of the upper triangle, lanes run over q >= p
+    if (tid < 4) {
+        Pk[tid] = D[NTL * 64 + tid];
+        if (tail.partials) tail.partials[tid] = Pk[tid];
+    }
+    for (int p = tid >> 5; p < m; p += nthr >> 5) {
+        const int row0 = 4 + p * m - p * (p - 1) / 2 - p;                    // index of (p, q) is row0 + q
+        for (int q = p + (tid & 31); q < m; q += 32) {
+            const double v = packed_pq<K, NB, HB, PM>(D, p, q);
+            Pk[row0 + q] = v;
+            if (tail.partials) tail.partials[row0 + q] = v;
+        }
     }
     __syncthreads();
     if (tail.mode == 0) return;
@@ -1002,37 +1005,16 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
     const double *Pfin = Pk;
     __shared__ unsigned timed_out;
     if (tid == 0) timed_out = 0u;
+    __syncthreads();
     if (tail.mode == 2) {
-        // all-reduce over NVLink peer memory: my vector -> slot `rank` of every rank's buffer (one warp per peer, remote
-        // stores), flag, wait for everybody's flag (bounded), sum the slots in rank order (same bits on every rank).
-        const int set = (int)(tail.epoch & 1u), world = tail.world, rank = tail.rank;
-        const int warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
-        for (int r = warp; r < world; r += nwarp) {
-            double *dst = reinterpret_cast<double *>(tail.peer_bufs[r]) + ((size_t)set * world + rank) * plen;
-            for (int e = lane; e < plen; e += 32) dst[e] = Pk[e];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < world)
-            st_release_sys_u32(reinterpret_cast<unsigned *>(tail.peer_flags[tid]) + (size_t)set * world + rank, tail.epoch);
+        // all-reduce over NVLink peer memory, low-latency protocol (device.cuh: ll_push / ll_reduce): one warp per peer
+        // stores my vector as 16-byte {lo, epoch, hi, epoch} units into slot `rank` of every rank's buffer; then every
+        // thread polls the tags of "its" elements in my own buffer and adds the world slots in rank order.
+        ll_push(tail.peer_bufs, tail.world, tail.rank, tail.epoch, plen, Pk);
         t2 = globaltimer_ns();
-        if (tid < world) {
-            const unsigned *fl = reinterpret_cast<const unsigned *>(tail.peer_flags[rank]) + (size_t)set * world + tid;
-            while (ld_acquire_sys_u32(fl) != tail.epoch) {
-                if (globaltimer_ns() - t2 > tail.timeout_ns) { timed_out = 1u; break; }
-                __nanosleep(32);
-            }
-        }
-        __threadfence_system();
+        if (!ll_reduce(tail.peer_bufs, tail.world, tail.rank, tail.epoch, plen, Pr, tail.timeout_ns)) timed_out = 1u;
         __syncthreads();
         t3 = globaltimer_ns();
-        const double *slots = reinterpret_cast<const double *>(tail.peer_bufs[rank]) + (size_t)set * world * plen;
-        for (int e = tid; e < plen; e += nthr) {
-            double v = 0.0;
-            for (int r = 0; r < world; ++r) v += __ldcv(slots + (size_t)r * plen + e);
-            Pr[e] = v;
-        }
-        __syncthreads();
         Pfin = Pr;
     }
     // estimators
@@ -1047,9 +1029,9 @@ __device__ __forceinline__ void fused_tail(const FusedTail &tail, double *__rest
         double *x = tail.res_host + rlen;
         x[0] = timed_out ? 1.0 : 0.0;
         x[1] = (double)(t1 - t0);                       // two-level combine (this CTA's share) + pack, ns
-        x[2] = (double)(t2 - t1);                       // peer stores + fence + flags
-        x[3] = (double)(t3 - t2);                       // wait for the peers
-        x[4] = (double)(globaltimer_ns() - t3);         // rank-order sum + estimators + result stores
+        x[2] = (double)(t2 - t1);                       // peer stores (issue)
+        x[3] = (double)(t3 - t2);                       // wait for the peers' elements + rank-order sum
+        x[4] = (double)(globaltimer_ns() - t3);         // estimators + result stores
         x[5] = (double)(ta - t0);                       // first-level combine (my group's rows)
         x[6] = (double)(tb - ta);                       // group row to HBM + fence + second-level ticket
         x[7] = (double)(tc - tb);                       // second-level combine
@@ -1142,8 +1124,15 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
     const uint64_t G = (uint64_t)gridDim.x * WS_E;
+    // E-warp e of this CTA takes batches first_batch(e), + G, + 2G, ...  The order is team-major (team = e / WS_S: every
+    // sub-partition has one E-warp of each team), so the warps that get one batch more than the others when nbatch is not a
+    // multiple of G are spread one per sub-partition: their last batch then runs alone on its FP64 pipe (~5.5 us) instead of
+    // sharing it with a second straggler (~10.8 us) -- at 8 GPUs (55.35 batches per warp) that is ~1 % of the step.
+    auto first_batch = [&](int e) -> uint64_t {
+        return (uint64_t)(e / WS_S) * ((uint64_t)gridDim.x * WS_S) + (uint64_t)blockIdx.x * WS_S + (uint64_t)(e % WS_S);
+    };
     auto count_of = [&](int e) -> uint64_t {
-        uint64_t g = (uint64_t)blockIdx.x * WS_E + e;
+        const uint64_t g = first_batch(e);
         return g < nbatch ? (nbatch - g + G - 1) / G : 0;
     };
     double sA = 0.0, qA = 0.0, sB = 0.0, qB = 0.0;
@@ -1160,7 +1149,7 @@ fused_wsd_kernel(SourceDev src, FusedConst<K> fc, F f, uint64_t i_begin, uint64_
         const double shift = shift_sh;
         const uint64_t basehi = table_basehi(terms);
         const uint64_t cnt = count_of(e);
-        uint64_t bt = (uint64_t)blockIdx.x * WS_E + e;
+        uint64_t bt = first_batch(e);
         // Phase alternation between the two E-warp teams (team = e / WS_S; every sub-partition has one warp of each).
         // Generation is bound by the SM-wide shared-memory pipe (random 8-byte table lookups cost 3-5 wavefronts
         // each), evaluation by the per-sub-partition FP64 pipe.  Left alone, the E-warps drift into lock-step --

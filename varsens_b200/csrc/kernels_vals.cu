@@ -391,51 +391,17 @@ __global__ void __launch_bounds__(256) finalize_kernel(int k, int l, double n, d
 
 // Partial-sum all-reduce over NVLink peer memory fused with the finalisation (see vs_allreduce_finalize_p2p); the stand-alone
 // form of the exchange the fused kernel runs in its tail (fused_impl.cuh: fused_tail), for partial sums that come from elsewhere
-// (two-phase path, user values).  Single CTA.  bufs[r] / flgs[r] are rank r's exchange buffer / flag array as mapped here.
+// (two-phase path, user values).  Single CTA; same low-latency protocol (device.cuh: ll_push / ll_reduce).
 // res[rlen] = 1.0 if a peer did not show up within timeout_ns (the indices are then meaningless), else 0.0.
 __global__ void __launch_bounds__(256) p2p_reduce_finalize_kernel(int k, int l, double n, double rows, int world, int rank,
-                                                                  const uint64_t *__restrict__ bufs, const uint64_t *__restrict__ flgs,
-                                                                  unsigned epoch, int plen, int rlen, unsigned long long timeout_ns,
-                                                                  const double *__restrict__ mine, int second_order,
-                                                                  double *__restrict__ reduced, double *__restrict__ res) {
-    const int set = (int)(epoch & 1u);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+                                                                  const uint64_t *__restrict__ bufs, unsigned epoch, int plen, int rlen,
+                                                                  unsigned long long timeout_ns, const double *__restrict__ mine,
+                                                                  int second_order, double *__restrict__ reduced, double *__restrict__ res) {
     __shared__ unsigned timed_out;
     if (threadIdx.x == 0) timed_out = 0u;
-    // 1. my partial sums -> slot `rank` of every rank's buffer: one warp per peer (remote stores over NVLink, posted)
-    for (int r = warp; r < world; r += nwarp) {
-        double *dst = reinterpret_cast<double *>(bufs[r]) + ((size_t)set * world + rank) * plen;
-        for (int e = lane; e < plen; e += 32) dst[e] = mine[e];
-    }
-    __threadfence_system();
     __syncthreads();
-    // 2. publish: flag[set][rank] = epoch on every rank; then wait (bounded) for everybody's flag in my own array
-    if (threadIdx.x < world) {
-        unsigned *f = reinterpret_cast<unsigned *>(flgs[threadIdx.x]) + (size_t)set * world + rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-    }
-    if (threadIdx.x < world) {
-        const unsigned *f = reinterpret_cast<const unsigned *>(flgs[rank]) + (size_t)set * world + threadIdx.x;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v == epoch) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > timeout_ns) { timed_out = 1u; break; }
-            __nanosleep(64);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 3. sum the slots in rank order (same order, hence same bits, on every rank)
-    const double *slots = reinterpret_cast<const double *>(bufs[rank]) + (size_t)set * world * plen;
-    for (int e = threadIdx.x; e < plen; e += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < world; ++r) s += __ldcv(slots + (size_t)r * plen + e);
-        reduced[e] = s;
-    }
+    ll_push(bufs, world, rank, epoch, plen, mine);
+    if (!ll_reduce(bufs, world, rank, epoch, plen, reduced, timeout_ns)) timed_out = 1u;
     __syncthreads();
     finalize_body(k, l, n, rows, reduced, second_order, res);
     if (threadIdx.x == 0) res[rlen] = timed_out ? 1.0 : 0.0;
@@ -447,7 +413,8 @@ int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t row
     VS_TRY(ensure(c, c->part_buf, (size_t)plen * sizeof(double)));
     VS_REQUIRE(partials < (const double *)c->part_buf.p || partials >= (const double *)c->part_buf.p + plen, VS_ERR_ARG,
                "partials_dev must not alias the exchange scratch");
-    p2p_reduce_finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, (double)rows, world, rank, peer_bufs_dev, peer_flags_dev, epoch,
+    (void)peer_flags_dev;
+    p2p_reduce_finalize_kernel<<<1, 256, 0, c->stream>>>(k, l, (double)n, (double)rows, world, rank, peer_bufs_dev, epoch,
                                                           plen, (int)result_len(k, l), (unsigned long long)c->opt.p2p_timeout_ms * 1000000ull,
                                                           partials, (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0,
                                                           (double *)c->part_buf.p, res_dev);

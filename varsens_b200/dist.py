@@ -54,9 +54,9 @@ def partials_layout(k, l=1):
 
 
 class PeerExchange(object):
-    """Exchange buffers for vs_allreduce_finalize_p2p: one torch symmetric-memory allocation per rank, mapped into every
-    process of the group over NVLink.  Layout per rank: 2 * world * plen doubles (slots, double-buffered on the epoch parity)
-    followed by 2 * world uint32 flags (padded to 16 doubles)."""
+    """Exchange buffers of the peer-memory all-reduce (vs_run_fused_p2p, vs_allreduce_finalize_p2p): one torch symmetric-memory
+    allocation per rank, mapped into every process of the group over NVLink.  Layout per rank: 2 sets (epoch parity) x world
+    slots x plen elements x 16 bytes -- every double travels as {lo, epoch, hi, epoch} (include/varsens_b200.h) -- zeroed."""
 
     def __init__(self, plen, device, group=None):
         import torch
@@ -67,15 +67,15 @@ class PeerExchange(object):
         self.rank = tdist.get_rank(self.group)
         self.plen = int(plen)
         nslots = 2 * self.world * self.plen
-        self.buf = symm.empty(nslots + 16 + 2 * self.world, dtype=torch.float64, device=device)
+        self.buf = symm.empty(2 * nslots + 16, dtype=torch.float64, device=device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, self.group)
         base = [int(p_) for p_ in self.handle.buffer_ptrs]
         self.peer_bufs = base
-        self.peer_flags = [b_ + 8 * nslots for b_ in base]
+        self.peer_flags = base                        # the low-latency protocol tags every element; no separate flag array
         self.epoch = 0
         torch.cuda.synchronize(device)
-        tdist.barrier(self.group)                     # every rank's buffer is zeroed before anybody publishes a flag
+        tdist.barrier(self.group)                     # every rank's buffer is zeroed before anybody stores into it
 
     def next_epoch(self):
         self.epoch += 1
