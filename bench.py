@@ -229,6 +229,10 @@ def run_gpu(args, rank, world):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, kernel_ms=None, wall_too=False):
+        """W untimed warm-up steps, then K timed steps bracketed by a barrier + synchronize on both sides.  Each step is timed on
+        the device (CUDA events on the stream the step runs on); the L2 flush between iterations is outside the events.  There
+        is no host barrier BETWEEN timed steps: at N>1 the exchange inside the step is the only synchronisation the ranks need
+        (a rank that is early waits in its kernel's tail, which the events include).  Returns the max over ranks of the mean."""
         for _ in range(warmup):
             fn()
             flush.zero_()
@@ -236,17 +240,15 @@ def run_gpu(args, rank, world):
         tot = 0.0
         res = None
         for _ in range(steps):
-            flush.zero_()                                               # L2 flush between timed iterations
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()                                          # untimed: ranks enter the step together
-                torch.cuda.synchronize()
+            flush.zero_()                                               # L2 flush between timed iterations (stream-ordered, untimed)
+            if wall_too:
+                torch.cuda.synchronize()                                # the host clock below must not see the flush
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
             res = fn()
             e1.record()
-            torch.cuda.synchronize()
+            e1.synchronize()
             wall = (time.perf_counter() - t0) * 1e3
             dev_ms = e0.elapsed_time(e1)
             tot += max(dev_ms, wall) if wall_too else dev_ms            # e2e includes the host-side call/return

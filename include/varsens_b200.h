@@ -153,6 +153,14 @@ int vs_sample_flat(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint3
                    const double *raw, int raw_mem, const vs_scale *scale, uint64_t row_begin,
                    uint64_t row_end, double *out, int out_mem);
 
+/* The BASE-ROW shard [i_begin,i_end) of every block of Sample.flat(): out[(t*rows + (i - i_begin))*k + c], t in [0, 2+2k),
+ * rows = i_end - i_begin -- i.e. the flat layout of the sub-design made of those base rows.  This is the multi-GPU split of
+ * export mode: rank r takes a contiguous range of base rows and generates only THOSE Halton points (a flat-row window of the
+ * same size needs the points of nearly all n base rows).  No collective.  Replaces varsens/saltelli.py:86-160, :184-193. */
+int vs_sample_flat_shard(vs_ctx *ctx, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                         const double *raw, int raw_mem, const vs_scale *scale, uint64_t i_begin, uint64_t i_end,
+                         double *out, int out_mem);
+
 /* ---- objective evaluation --------------------------------------------------------------------- */
 /* Objective values of base rows [i_begin,i_end) for a registered functor, sample rows generated on
  * the fly (never stored): fvals[(t*rows + (i-i_begin))], t in [0,2+2k), rows = i_end-i_begin --

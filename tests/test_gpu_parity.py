@@ -158,6 +158,37 @@ def test_sample_flat_windows_and_device_buffers(ctx):
         ctx.sample_flat(k, n, perm_of(n), 5, row_begin=5, row_end=total + 1)
 
 
+@pytest.mark.parametrize("k,n,discard", [(6, 1024, 0), (50, 300, 3), (20, 333, 11), (2, 70, 0), (64, 40, 0), (5, 200, 1), (7, 64, 0)])
+def test_sample_flat_shard_and_bulk_kernel(ctx, k, n, discard, monkeypatch):
+    """Export mode: the TMA bulk-store kernel (even k), the scalar-store kernel (odd k, VS_NO_BULK_EXPORT=1) and the base-row
+    shard addressing (vs_sample_flat_shard: a rank's share of every block) all reproduce the oracle's Sample.flat() bit for bit."""
+    import torch
+    from varsens_b200 import _cabi
+    p = perm_of(n)
+    lb, ub = numpy.linspace(-1.0, 0.5, k), numpy.linspace(1.0, 3.0, k)
+    for scale, oscale_ in ((_cabi.IDENTITY, None), (_cabi.Scale(_cabi.SCALE_LINEAR, lb, ub), ("linear", lb, ub))):
+        whole = cport.sample_flat(k, n, discard, scale=oscale_)
+        total = 2 * n * (1 + k)
+        assert (ctx.sample_flat(k, n, p, discard, scale) == whole).all()
+        for lo, hi in ((0, 1), (n - 1, n + 2), (3, total - 5), (2 * n + 7, 2 * n + 7 + 3 * n + 1), (total - 1, total)):
+            assert (ctx.sample_flat(k, n, p, discard, scale, row_begin=lo, row_end=hi) == whole[lo:hi]).all(), (lo, hi)
+        monkeypatch.setenv("VS_NO_BULK_EXPORT", "1")
+        ctx.reload_env()
+        assert (ctx.sample_flat(k, n, p, discard, scale, row_begin=3, row_end=total - 5) == whole[3:total - 5]).all()
+        monkeypatch.delenv("VS_NO_BULK_EXPORT")
+        ctx.reload_env()
+        blocks = whole.reshape(2 + 2 * k, n, k)
+        for lo, hi in ((0, n), (0, 1), (n // 3, n // 3 + 33), (n - 5, n), (7, 7)):
+            got = ctx.sample_flat_shard(k, n, p, lo, hi, discard, scale)
+            assert got.shape == (2 + 2 * k, hi - lo, k) and (got == blocks[:, lo:hi, :]).all(), (lo, hi)
+        # device output, with an offset that is only 8-byte aligned (falls back to the scalar-store kernel)
+        buf = torch.empty((2 + 2 * k) * 40 * k + 1, dtype=torch.float64, device="cuda")
+        hi = min(n, 40)
+        out = buf[1:1 + (2 + 2 * k) * hi * k].view(2 + 2 * k, hi, k)
+        ctx.sample_flat_shard(k, n, torch.from_numpy(p.astype(numpy.int32)).cuda(), 0, hi, discard, scale, out=out)
+        assert (out.cpu().numpy() == blocks[:, :hi, :]).all()
+
+
 def test_sample_flat_large_property(ctx):
     """Structure at a size the oracle cannot hold (k=50, n=2^16 -> 2.7 GB on device): column-substitution
     identities of saltelli.py:119-123 checked on the device with torch, plus a checksum of checksums."""

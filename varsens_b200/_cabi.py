@@ -25,7 +25,7 @@ SYMBOLS = (
     "vs_halton", "vs_sobol", "vs_sample_flat", "vs_eval_values", "vs_partials_from_values", "vs_finalize",
     "vs_finalize_device", "vs_allreduce_finalize_p2p", "vs_indices_from_values", "vs_fused_partials", "vs_run_fused", "vs_measure_fp64_peak", "vs_last_kernel_ms",
     "vs_ctx_reload_env", "vs_ctx_set_halton_mode", "vs_halton_terms_mode", "vs_run_fused_p2p", "vs_last_tail_ns",
-    "vs_halton_arith_check", "vs_reference_permutation", "vs_ctx_set_timing",
+    "vs_halton_arith_check", "vs_reference_permutation", "vs_ctx_set_timing", "vs_sample_flat_shard",
 )
 HALTON_DIVIDE, HALTON_RECIPROCAL, HALTON_RUNNING_RECIPROCAL, HALTON_HORNER = 0, 1, 2, 3
 ERR_TIMEOUT = 6
@@ -93,6 +93,7 @@ def lib():
         L.vs_last_tail_ns.argtypes = [vp, i32, vp]
         L.vs_halton_arith_check.argtypes = [i32, i32]
         L.vs_ctx_set_timing.argtypes = [vp, i32]
+        L.vs_sample_flat_shard.argtypes = [vp, i32, u64, u64, vp, i32, vp, i32, P(vs_scale), u64, u64, vp, i32]
         L.vs_reference_permutation.argtypes = [u64, ctypes.c_uint32, vp, vp, P(i32)]
         L.vs_measure_fp64_peak.argtypes = [vp, P(ctypes.c_double)]
         L.vs_last_kernel_ms.argtypes = [vp, P(ctypes.c_float)]
@@ -325,6 +326,18 @@ class Context(object):
         op, om, _ = buf(out, numpy.float64, out=True)
         check(lib().vs_sample_flat(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(row_begin),
                                    int(row_end), op, om))
+        return out
+
+    def sample_flat_shard(self, k, n, perm, i_begin, i_end, discard=0, scale=IDENTITY, raw=None, out=None):
+        """Base rows [i_begin,i_end) of EVERY block of Sample.flat(): (2+2k, i_end-i_begin, k) -- a rank's share in multi-GPU
+        export mode (vs_sample_flat_shard)."""
+        rows = int(i_end - i_begin)
+        out = numpy.empty((2 + 2 * int(k), rows, int(k))) if out is None else out
+        sp, keep = scale.c_struct(k)
+        pp, pm, pk = buf(perm, numpy.uint32)
+        rp, rm, rk = buf(raw, numpy.float64)
+        op, om, _ = buf(out, numpy.float64, out=True)
+        check(lib().vs_sample_flat_shard(self._h, int(k), int(n), int(discard), pp, pm, rp, rm, sp, int(i_begin), int(i_end), op, om))
         return out
 
     # ---- objective values / estimators --------------------------------------------------------

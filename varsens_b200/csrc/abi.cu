@@ -139,6 +139,27 @@ extern "C" int vs_sample_flat(vs_ctx *c, int k, uint64_t n, uint64_t discard, co
     return VS_OK;
 }
 
+extern "C" int vs_sample_flat_shard(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
+                                    const double *raw, int raw_mem, const vs_scale *scale, uint64_t i_begin, uint64_t i_end,
+                                    double *out, int out_mem) {
+    VS_TRY(check_common(c, k));
+    VS_REQUIRE(n >= 1 && i_begin <= i_end && i_end <= n, VS_ERR_ARG, "bad base-row range [%llu,%llu) of %llu",
+               (unsigned long long)i_begin, (unsigned long long)i_end, (unsigned long long)n);
+    if (i_begin == i_end) return VS_OK;
+    VS_REQUIRE(out, VS_ERR_ARG, "out is NULL");
+    SourceDev src;
+    VS_TRY(make_source(c, k, n, discard, perm, perm_mem, i_begin, i_end - i_begin, raw, raw_mem, &src));
+    ScaleDev s;
+    VS_TRY(get_scale(c, k, scale, &s));
+    OutStage o{c, out, out_mem, (i_end - i_begin) * (uint64_t)(2 + 2 * k) * (uint64_t)k * sizeof(double)};
+    VS_TRY(o.begin(c->io_buf));
+    VS_TRY(launch_sample_shard(c, k, src, s, i_begin, i_end, (double *)o.dev));
+    VS_TRY(o.end());
+    if (out_mem == VS_MEM_DEVICE && (perm_mem == VS_MEM_HOST || (raw && raw_mem == VS_MEM_HOST)))
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+    return VS_OK;
+}
+
 extern "C" int vs_eval_values(vs_ctx *c, int k, uint64_t n, uint64_t discard, const uint32_t *perm, int perm_mem,
                               const double *raw, int raw_mem, const vs_scale *scale, int objective, const double *params,
                               int n_params, uint64_t i_begin, uint64_t i_end, double *fvals, int fvals_mem) {

@@ -1389,9 +1389,8 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
             tail.partials = partials;
             tail.mode = req ? req->mode : 0;
             if (tail.mode >= 1) {
-                VS_TRY(ensure(c, c->res_buf, (size_t)RLEN * sizeof(double)));
                 VS_TRY(ensure_host_res(c, (size_t)RLEN + HOST_RES_EXTRA));
-                tail.res_dev = (double *)c->res_buf.p;
+                tail.res_dev = nullptr;                              // results go straight to mapped host memory
                 tail.res_host = c->host_res;
                 tail.n_total = (double)req->n_total;
                 tail.rows_total = (double)req->rows_total;

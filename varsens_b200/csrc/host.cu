@@ -76,6 +76,7 @@ void load_options(Options &o) {
     o.p2p_timeout_ms = env_int("VS_P2P_TIMEOUT_MS", 10000);
     o.halton_mode = env_int("VS_HALTON_MODE", 0);
     o.index_bits = env_int("VS_INDEX_BITS", 0);
+    o.no_bulk_export = env_int("VS_NO_BULK_EXPORT", 0);
 }
 
 // Mapped pinned host memory the tail of the fused kernel writes its results to (no device-to-host copy call on the step).

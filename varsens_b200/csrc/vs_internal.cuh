@@ -122,6 +122,7 @@ struct Options {
     int p2p_timeout_ms = 10000; // VS_P2P_TIMEOUT_MS bounded wait for the peers' flags in the exchange
     int halton_mode = 0;        // VS_HALTON_MODE    term-table arithmetic (enum vs_halton_mode)
     int index_bits = 0;         // VS_INDEX_BITS=32 forces the general (32-bit index) fused kernel
+    int no_bulk_export = 0;     // VS_NO_BULK_EXPORT=1: export mode through the scalar-store kernel
 };
 
 // What the tail of the fused kernel has to do after the CTA partial sums are complete (host side of FusedTail).
@@ -185,6 +186,7 @@ int launch_sobol(vs_ctx *c, int k, uint64_t first, uint64_t count, const uint32_
                  const ScaleDev &s, double *out);
 int launch_sample_flat(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, uint64_t row_begin,
                        uint64_t row_end, double *out);
+int launch_sample_shard(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, uint64_t i_begin, uint64_t i_end, double *out);
 // kernels_vals.cu
 int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const ObjectiveDev &o,
                        uint64_t i_begin, uint64_t i_end, double *fvals);
