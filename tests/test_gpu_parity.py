@@ -178,7 +178,7 @@ def test_sample_flat_shard_and_bulk_kernel(ctx, k, n, discard, monkeypatch):
         monkeypatch.delenv("VS_NO_BULK_EXPORT")
         ctx.reload_env()
         blocks = whole.reshape(2 + 2 * k, n, k)
-        for lo, hi in ((0, n), (0, 1), (n // 3, n // 3 + 33), (n - 5, n), (7, 7)):
+        for lo, hi in ((0, n), (0, 1), (n // 3, min(n, n // 3 + 33)), (n - 5, n), (7, 7)):
             got = ctx.sample_flat_shard(k, n, p, lo, hi, discard, scale)
             assert got.shape == (2 + 2 * k, hi - lo, k) and (got == blocks[:, lo:hi, :]).all(), (lo, hi)
         # device output, with an offset that is only 8-byte aligned (falls back to the scalar-store kernel)
@@ -186,6 +186,7 @@ def test_sample_flat_shard_and_bulk_kernel(ctx, k, n, discard, monkeypatch):
         hi = min(n, 40)
         out = buf[1:1 + (2 + 2 * k) * hi * k].view(2 + 2 * k, hi, k)
         ctx.sample_flat_shard(k, n, torch.from_numpy(p.astype(numpy.int32)).cuda(), 0, hi, discard, scale, out=out)
+        ctx.synchronize()                                       # device output: the call only enqueues on the ctx stream
         assert (out.cpu().numpy() == blocks[:, :hi, :]).all()
 
 
@@ -417,6 +418,35 @@ def test_eval_values_and_rk4(ctx):
     got = ctx.eval_values(6, 100, perm_of(100), cport.OBJ_GFUNCTION, A6, i_begin=10, i_end=77)
     want = cport.values(6, 100, cport.OBJ_GFUNCTION, A6, i0=10, i1=77)
     numpy.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+@pytest.mark.parametrize("k,n", [(24, 200), (50, 700), (11, 64), (12, 33), (100, 70), (3, 1000)])
+def test_eval_values_product_form_kernel(ctx, k, n, monkeypatch):
+    """Two-phase path, product-form kernel (prefix * term * suffix per row, computed Halton terms for bases >= 37) against the
+    oracle's point-by-point values: same products, different association -> a few ulp; and against the point-by-point kernel."""
+    from varsens_b200 import _cabi
+    a = ([0, 0.5, 3, 9, 99, 99] * 20)[:k]
+    p = perm_of(n)
+    lb, ub = numpy.linspace(0.1, 0.3, k), numpy.linspace(0.6, 0.95, k)
+    for scale, osc, disc in ((_cabi.IDENTITY, None, 0), (_cabi.Scale(_cabi.SCALE_LINEAR, lb, ub), ("linear", lb, ub), 13)):
+        want = cport.values(k, n, cport.OBJ_GFUNCTION, a, discard=disc, scale=osc)
+        got = ctx.eval_values(k, n, p, cport.OBJ_GFUNCTION, a, discard=disc, scale=scale)
+        numpy.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+        lo, hi = n // 3, n - 1
+        part = ctx.eval_values(k, n, p, cport.OBJ_GFUNCTION, a, discard=disc, scale=scale, i_begin=lo, i_end=hi)
+        assert (part == got[:, lo:hi]).all()
+        monkeypatch.setenv("VS_NO_PF_EVAL", "1")
+        ctx.reload_env()
+        old = ctx.eval_values(k, n, p, cport.OBJ_GFUNCTION, a, discard=disc, scale=scale)
+        monkeypatch.delenv("VS_NO_PF_EVAL")
+        ctx.reload_env()
+        numpy.testing.assert_allclose(got, old, rtol=1e-13, atol=0)
+    raw = numpy.random.RandomState(k).rand(2 * n, k)
+    numpy.testing.assert_allclose(ctx.eval_values(k, n, p, cport.OBJ_GFUNCTION, a, raw=raw),
+                                  cport.values(k, n, cport.OBJ_GFUNCTION, a, raw=raw), rtol=1e-13, atol=0)
+    if k > 20:                                                       # indices through the whole two-phase path
+        res = ctx.run_fused(k, n, p, cport.OBJ_GFUNCTION, a)
+        assert_indices(res, cport.run(k, n, cport.OBJ_GFUNCTION, a))
 
 
 def test_c5_rk4_frozen_spec_all_indices(ctx):

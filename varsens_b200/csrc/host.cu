@@ -77,6 +77,7 @@ void load_options(Options &o) {
     o.halton_mode = env_int("VS_HALTON_MODE", 0);
     o.index_bits = env_int("VS_INDEX_BITS", 0);
     o.no_bulk_export = env_int("VS_NO_BULK_EXPORT", 0);
+    o.no_pf_eval = env_int("VS_NO_PF_EVAL", 0);
 }
 
 // Mapped pinned host memory the tail of the fused kernel writes its results to (no device-to-host copy call on the step).
@@ -228,7 +229,10 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         size_t nb_terms = terms.size() * sizeof(double), nb_magic = (size_t)k * 8, nb_u32 = (size_t)k * 4;
         size_t nb_fixed = ((fixed.size() + 1) & ~(size_t)1) * sizeof(double);
         nb_terms = (nb_terms + 15) & ~(size_t)15;
-        size_t total = nb_terms + nb_fixed + nb_magic + 2 * nb_u32 + 64;
+        std::vector<double> arh_h, arl_h;
+        const bool arith_ok = build_arith(bases, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, arh_h, arl_h);
+        const size_t nb_ar = arh_h.size() * sizeof(double);
+        size_t total = nb_terms + nb_fixed + 2 * nb_ar + nb_magic + 2 * nb_u32 + 64;
         if (hc.blob) {
             VS_CUDA(cudaStreamSynchronize(c->stream));
             VS_CUDA(cudaFree(hc.blob));
@@ -243,6 +247,13 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         hc.dev.fixed = fixed.empty() ? nullptr : (const double *)p;
         hc.dev.fixed_len = (uint32_t)fixed.size();
         p += nb_fixed;
+        VS_CUDA(cudaMemcpy(p, arh_h.data(), nb_ar, cudaMemcpyHostToDevice));
+        hc.dev.arh = (const double *)p;
+        p += nb_ar;
+        VS_CUDA(cudaMemcpy(p, arl_h.data(), nb_ar, cudaMemcpyHostToDevice));
+        hc.dev.arl = (const double *)p;
+        p += nb_ar;
+        hc.dev.arith_ok = arith_ok ? 1 : 0;
         VS_CUDA(cudaMemcpy(p, magic.data(), nb_magic, cudaMemcpyHostToDevice));
         hc.dev.magic = (const uint64_t *)p;
         p += nb_magic;
@@ -255,7 +266,9 @@ int get_halton(vs_ctx *c, int k, uint64_t max_index, HaltonDev *out) {
         hc.k = k;
         hc.mode = mode;
         hc.ndigits = nd;
-        hc.arith_ok = build_arith(bases, mode == VS_HALTON_HORNER ? VS_HALTON_DIVIDE : mode, hc.arh, hc.arl);
+        hc.arh = arh_h;
+        hc.arl = arl_h;
+        hc.arith_ok = arith_ok;
     }
     hc.dev.mode = mode;
     *out = hc.dev;

@@ -191,7 +191,7 @@ __device__ __forceinline__ void ex_commit() { asm volatile("cp.async.bulk.commit
 template <int N> __device__ __forceinline__ void ex_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void ex_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int EX_THREADS = 256, EX_GEN = EX_THREADS - 32;
+constexpr int EX_THREADS = 512, EX_GEN = EX_THREADS - 32;
 
 __global__ void __launch_bounds__(EX_THREADS, 1)
 sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restrict__ out) {
@@ -229,35 +229,54 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
 
     if (warp != 0) {
         // ------------------------------------------ generators ------------------------------------------
-        const int gt = tid - 32;
+        // lane = tile row, warp = a set of dimensions: all lanes of a warp walk the SAME base, so the digit loop has one trip
+        // count per warp (no divergence), the base / magic / table row are warp-uniform, and the A chain (consecutive indices:
+        // conflict-free table reads) and the B chain (permuted indices) of a row advance together as two independent chains.
+        const int gw = warp - 1;
         for (uint64_t it = 0; it < my_tiles; ++it) {
             const int pb = (int)(it & 1);
             const uint64_t i0 = g.i_lo + (blockIdx.x + it * gridDim.x) * (uint64_t)TI;
             const int rows = (int)((i0 + TI <= g.i_hi) ? TI : (g.i_hi - i0));
             double *A = tiles + (size_t)(2 * pb) * tile, *B = A + tile;
+            const bool live = lane < rows;
+            const uint64_t i = i0 + (live ? lane : 0);
+            const uint64_t pi = src.perm[i];
             ex_bar_wait(bars + 2 + pb, (uint32_t)(((it >> 1) & 1) ^ 1));                 // the store warp is done with this buffer pair
-            const int cells = rows * k;
-            int r = gt / k, d = gt - r * k;
-            const int dr = EX_GEN / k, dd = EX_GEN - dr * k;
-            for (int e = gt; e < cells; e += EX_GEN) {
-                const uint64_t i = i0 + r;
+            for (int d = gw; d < k; d += EX_GEN / 32) {
                 double pa, pbv;
                 if (src.raw) {
                     pa = src.raw[i * (uint64_t)k + d];
-                    pbv = src.raw[(n + src.perm[i]) * (uint64_t)k + d];
-                } else if (src.h.mode == VS_HALTON_HORNER) {
-                    pa = radical_inverse_horner(sbase[d], smagic[d], (uint32_t)(src.start + i));
-                    pbv = radical_inverse_horner(sbase[d], smagic[d], (uint32_t)(src.start + n + src.perm[i]));
+                    pbv = src.raw[(n + pi) * (uint64_t)k + d];
                 } else {
-                    pa = radical_inverse(T + soff[d], sbase[d], smagic[d], (uint32_t)(src.start + i));
-                    pbv = radical_inverse(T + soff[d], sbase[d], smagic[d], (uint32_t)(src.start + n + src.perm[i]));
+                    const uint32_t b = sbase[d];
+                    const uint64_t magic = smagic[d];
+                    uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
+                    if (src.h.mode == VS_HALTON_HORNER) {
+                        pa = radical_inverse_horner(b, magic, ma);
+                        pbv = radical_inverse_horner(b, magic, mb);
+                    } else if (b == 2u) {
+                        pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
+                        pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
+                    } else {
+                        const double *row = T + soff[d];
+                        pa = 0.0;
+                        pbv = 0.0;
+                        while ((ma | mb) != 0u) {                       // an exhausted index keeps adding row[0] == 0.0: exact
+                            const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
+                            pa = __dadd_rn(pa, row[ma - qa * b]);
+                            pbv = __dadd_rn(pbv, row[mb - qb * b]);
+                            row += b;
+                            ma = qa;
+                            mb = qb;
+                        }
+                    }
                 }
                 if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pbv = __dadd_rn(__dmul_rn(pbv, swr[d]), slb[d]); }
                 else if (s.kind == VS_SCALE_POWER) { pa = __dmul_rn(slb[d], pow(swr[d], pa)); pbv = __dmul_rn(slb[d], pow(swr[d], pbv)); }
-                A[e] = pa;
-                B[e] = pbv;
-                r += dr; d += dd;
-                if (d >= k) { d -= k; ++r; }
+                if (live) {
+                    A[(size_t)lane * k + d] = pa;
+                    B[(size_t)lane * k + d] = pbv;
+                }
             }
             ex_fence_async();                                   // my tile entries must be visible to the TMA (async proxy)
             __syncwarp();
@@ -288,38 +307,59 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             }
             if (lane == 0) ex_bulk_store(out + orow * (uint64_t)k, buf + (size_t)r0 * k, (uint32_t)((r1 - r0) * k * 8));
         };
-        put(1, B);                                              // M_2 first: B is the tile that gets patched first below
-        if (lane == 0) ex_commit();
-        put(0, A);                                              // M_1
-        if (lane == 0) ex_commit();
-        double a_prev = 0.0, b_prev = 0.0;
+        // does block t of this tile intersect the window?  (blocks outside it cost nothing: no patch, no fence, no wait)
+        auto wanted = [&](int t) {
+            if (g.mode != 0) return true;
+            const uint64_t R0 = (uint64_t)t * n + i0;
+            return !(R0 + rows <= g.row_begin || R0 >= g.row_end);
+        };
+        int last = -1;                                          // tile of the most recent bulk group: 0 = A, 1 = B
+        int pa_col = -1, pb_col = -1;                           // column currently patched in A / B
+        double pa_val = 0.0, pb_val = 0.0;                      // ... and its original value (this lane's row)
+        // Before a tile changes, its own last bulk read must have drained: if the newest group belongs to the OTHER tile,
+        // "all but one group done" is enough (that one keeps streaming while we patch), else everything has to be done.
+        auto quiesce = [&](int tilesel) {
+            if (lane == 0) {
+                if (last == tilesel) ex_wait_read<0>();
+                else ex_wait_read<1>();
+            }
+            __syncwarp();
+        };
+        if (wanted(1)) { put(1, B); if (lane == 0) ex_commit(); last = 1; }          // M_2
+        if (wanted(0)) { put(0, A); if (lane == 0) ex_commit(); last = 0; }          // M_1
         for (int j = 0; j < k; ++j) {
-            const double a_j = lane < rows ? A[(size_t)lane * k + j] : 0.0;     // a previous patch never touches column j
+            const bool nb = wanted(2 + j), na = wanted(2 + k + j);
+            if (!nb && !na) continue;
+            const double a_j = lane < rows ? A[(size_t)lane * k + j] : 0.0;     // column j is never the patched one (pa_col, pb_col < j)
             const double b_j = lane < rows ? B[(size_t)lane * k + j] : 0.0;
-            // N_j[j] = B with column j from A: B's previous bulk read must have drained before B changes
-            if (lane == 0) ex_wait_read<1>();
-            __syncwarp();
-            if (lane < rows) {
-                if (j > 0) B[(size_t)lane * k + j - 1] = b_prev;
-                B[(size_t)lane * k + j] = a_j;
+            if (nb) {                                           // N_j[j] = B with column j from A
+                quiesce(1);
+                if (lane < rows) {
+                    if (pb_col >= 0) B[(size_t)lane * k + pb_col] = pb_val;
+                    B[(size_t)lane * k + j] = a_j;
+                }
+                pb_col = j;
+                pb_val = b_j;
+                ex_fence_async();
+                __syncwarp();
+                put(2 + j, B);
+                if (lane == 0) ex_commit();
+                last = 1;
             }
-            ex_fence_async();
-            __syncwarp();
-            put(2 + j, B);
-            if (lane == 0) ex_commit();
-            // N_nj[j] = A with column j from B
-            if (lane == 0) ex_wait_read<1>();
-            __syncwarp();
-            if (lane < rows) {
-                if (j > 0) A[(size_t)lane * k + j - 1] = a_prev;
-                A[(size_t)lane * k + j] = b_j;
+            if (na) {                                           // N_nj[j] = A with column j from B
+                quiesce(0);
+                if (lane < rows) {
+                    if (pa_col >= 0) A[(size_t)lane * k + pa_col] = pa_val;
+                    A[(size_t)lane * k + j] = b_j;
+                }
+                pa_col = j;
+                pa_val = a_j;
+                ex_fence_async();
+                __syncwarp();
+                put(2 + k + j, A);
+                if (lane == 0) ex_commit();
+                last = 0;
             }
-            ex_fence_async();
-            __syncwarp();
-            put(2 + k + j, A);
-            if (lane == 0) ex_commit();
-            a_prev = a_j;
-            b_prev = b_j;
         }
         if (lane == 0) ex_wait_read<0>();                       // both tiles may be overwritten by the generators now
         __syncwarp();

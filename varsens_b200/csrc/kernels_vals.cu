@@ -2,6 +2,7 @@
 #include "device.cuh"
 
 #include <type_traits>
+#include <vector>
 
 namespace vs {
 
@@ -84,6 +85,163 @@ __global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, Scal
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-phase path, phase 1, product-form functors (f(x) = prod_c term(c, x_c): the g-function), any k that fits.
+// A CTA (8 warps) works on 32 base rows at a time, lane = row:
+//   P1  warp w takes dimensions w, w+8, ...: Halton digit sums of A_i and B_i as two independent chains with warp-uniform base
+//       (terms of the bases < 37 from a small shared table, terms of the larger bases COMPUTED from double-double reciprocals --
+//       bit-identical to the table, host.cu: build_arith -- so no 160 KB table has to live in shared memory), scaling, and the
+//       functor's term -> TA[d][row], TB[d][row];
+//   P2  four warps run the four product chains over d (lane = row): prefix of TA, prefix of TB, suffix of TA, suffix of TB;
+//   P3  warp w takes j = w, w+8, ...: f(N_j[j]) = PB[j] * TA[j] * SB[j+1], f(N_nj[j]) = PA[j] * TB[j] * SA[j+1], stored as
+//       256-byte coalesced runs of the t-major value layout; f(M_1) = PA[k], f(M_2) = PB[k].
+// O(k) multiplies per row instead of the O(k^2) of point-by-point evaluation: C4's second-order block went from 13 ms in
+// this phase to ~1.5 (tools/bench_configs.py).  The values are the same products associated differently (prefix * term *
+// suffix instead of left to right): <= 2 ulp from F::operator(), far inside the 1e-10 contract on the indices.
+// ---------------------------------------------------------------------------------------------
+constexpr int PF_AR_D0 = 11, PF_AR_J = 7, PF_WARPS = 8;
+
+template <class F>
+__global__ void __launch_bounds__(PF_WARPS * 32, 2)
+eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end, uint32_t table_len, double *__restrict__ fvals) {
+    extern __shared__ __align__(16) double smem[];
+    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
+    uint32_t *sbase = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *soff = sbase + k;
+    uint64_t *smagic = reinterpret_cast<uint64_t *>(smem + ((2 * k + 1) / 2));
+    double *slb = reinterpret_cast<double *>(smagic + k);
+    double *swr = slb + k;
+    double *sarh = swr + k, *sarl = sarh + (size_t)k * PF_AR_J;
+    double *table = sarl + (size_t)k * PF_AR_J;
+    double *TA = table + table_len, *TB = TA + (size_t)k * 32;
+    double *PA = TB + (size_t)k * 32, *PB = PA + (size_t)(k + 1) * 32, *SA = PB + (size_t)(k + 1) * 32, *SB = SA + (size_t)(k + 1) * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (!src.raw) {
+        for (int d = tid; d < k; d += blockDim.x) { sbase[d] = src.h.base[d]; soff[d] = src.h.off[d]; smagic[d] = src.h.magic[d]; }
+        for (int e = tid; e < k * PF_AR_J; e += blockDim.x) { sarh[e] = src.h.arh[e]; sarl[e] = src.h.arl[e]; }
+        for (uint32_t e = tid; e < table_len; e += blockDim.x) table[e] = src.h.terms[e];
+    }
+    for (int d = tid; d < k; d += blockDim.x) {
+        slb[d] = s.kind != VS_SCALE_IDENTITY ? s.lb[d] : 0.0;
+        swr[d] = s.kind != VS_SCALE_IDENTITY ? s.wr[d] : 1.0;
+    }
+    __syncthreads();
+    const uint64_t rows = i_end - i_begin, n = src.n;
+    const uint64_t ntiles = (rows + 31) / 32;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t r = tile * 32 + lane;
+        const bool live = r < rows;
+        const uint64_t i = i_begin + (live ? r : rows - 1);
+        const uint64_t pi = src.perm[i];
+        // ---- P1: coordinates and terms
+        for (int d = warp; d < k; d += PF_WARPS) {
+            double pa, pb;
+            if (src.raw) {
+                pa = src.raw[i * (uint64_t)k + d];
+                pb = src.raw[(n + pi) * (uint64_t)k + d];
+            } else {
+                const uint32_t b = sbase[d];
+                const uint64_t magic = smagic[d];
+                uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
+                if (b == 2u) {
+                    pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
+                    pb = (double)__brev(mb) * 2.3283064365386962890625e-10;
+                } else if (d < PF_AR_D0) {
+                    const double *row = table + soff[d];
+                    pa = 0.0;
+                    pb = 0.0;
+                    while ((ma | mb) != 0u) {                           // an exhausted index keeps adding row[0] == 0.0: exact
+                        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
+                        pa = __dadd_rn(pa, row[ma - qa * b]);
+                        pb = __dadd_rn(pb, row[mb - qb * b]);
+                        row += b;
+                        ma = qa;
+                        mb = qb;
+                    }
+                } else {
+                    // computed terms: digit / b^(j+1) = fma(dd, rh, dd * rl), dd = 8 * digit (fused_impl.cuh: digit_step_arith)
+                    const double *rh = sarh + (size_t)d * PF_AR_J, *rl = sarl + (size_t)d * PF_AR_J;
+                    pa = 0.0;
+                    pb = 0.0;
+                    for (int j = 0; (ma | mb) != 0u; ++j) {
+                        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
+                        const double da = (double)(8u * (ma - qa * b)), db = (double)(8u * (mb - qb * b));
+                        pa = __dadd_rn(pa, __fma_rn(da, rh[j], __dmul_rn(da, rl[j])));
+                        pb = __dadd_rn(pb, __fma_rn(db, rh[j], __dmul_rn(db, rl[j])));
+                        ma = qa;
+                        mb = qb;
+                    }
+                }
+            }
+            if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pb = __dadd_rn(__dmul_rn(pb, swr[d]), slb[d]); }
+            else if (s.kind == VS_SCALE_POWER) { pa = __dmul_rn(slb[d], pow(swr[d], pa)); pb = __dmul_rn(slb[d], pow(swr[d], pb)); }
+            TA[(size_t)d * 32 + lane] = f.term(d, pa);
+            TB[(size_t)d * 32 + lane] = f.term(d, pb);
+        }
+        __syncthreads();
+        // ---- P2: four product chains, lane = row
+        if (warp < 4) {
+            const double *Tm = (warp & 1) ? TB : TA;
+            if (warp < 2) {
+                double *P = warp ? PB : PA;
+                double p = 1.0;
+                P[lane] = p;
+                for (int c = 0; c < k; ++c) { p *= Tm[(size_t)c * 32 + lane]; P[(size_t)(c + 1) * 32 + lane] = p; }
+            } else {
+                double *S = (warp & 1) ? SB : SA;
+                double p = 1.0;
+                S[(size_t)k * 32 + lane] = p;
+                for (int c = k - 1; c >= 0; --c) { p *= Tm[(size_t)c * 32 + lane]; S[(size_t)c * 32 + lane] = p; }
+            }
+        }
+        __syncthreads();
+        // ---- P3: the 2 + 2k values of every row
+        if (live) {
+            if (warp == 0) fvals[r] = PA[(size_t)k * 32 + lane];                                   // f(M_1[i])
+            if (warp == 1) fvals[rows + r] = PB[(size_t)k * 32 + lane];                            // f(M_2[i])
+            for (int j = warp; j < k; j += PF_WARPS) {
+                const double vj = PB[(size_t)j * 32 + lane] * TA[(size_t)j * 32 + lane] * SB[(size_t)(j + 1) * 32 + lane];   // M_2 with column j from M_1
+                const double vn = PA[(size_t)j * 32 + lane] * TB[(size_t)j * 32 + lane] * SA[(size_t)(j + 1) * 32 + lane];   // M_1 with column j from M_2
+                fvals[(uint64_t)(2 + j) * rows + r] = vj;
+                fvals[(uint64_t)(2 + k + j) * rows + r] = vn;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class F>
+static int launch_eval_pf(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const F &f, uint64_t i_begin, uint64_t i_end,
+                          double *fvals, bool *done) {
+    *done = false;
+    const uint64_t rows = i_end - i_begin;
+    if (rows == 0 || c->opt.no_pf_eval) return VS_OK;
+    if (!src.raw && (src.h.mode == VS_HALTON_HORNER || !src.h.arith_ok)) return VS_OK;
+    uint32_t table_len = 0;
+    if (!src.raw) {
+        // the table prefix of the dimensions below PF_AR_D0 (terms are laid out dimension by dimension: b_d * ndigits_d each)
+        static const uint32_t small_primes[PF_AR_D0] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
+        table_len = 0;
+        for (int d = 0; d < k && d < PF_AR_D0; ++d) table_len += small_primes[d] * c->halton.ndigits[d];
+        if (k <= PF_AR_D0) table_len = src.h.total_terms;
+    }
+    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + table_len + 2 * (size_t)k * 32 +
+                           4 * (size_t)(k + 1) * 32 + 2;
+    const size_t smem = doubles * sizeof(double);
+    if (smem > c->smem_optin) return VS_OK;
+    VS_CUDA(cudaFuncSetAttribute(eval_values_pf_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t ntiles = (rows + 31) / 32;
+    const int per_sm = smem * 2 + 2048 <= c->smem_optin ? 2 : 1;
+    const unsigned grid = (unsigned)(ntiles < (uint64_t)(per_sm * c->sm_count) ? ntiles : (uint64_t)(per_sm * c->sm_count));
+    time_begin(c);
+    eval_values_pf_kernel<F><<<grid, PF_WARPS * 32, smem, c->stream>>>(k, src, s, f, i_begin, i_end, table_len, fvals);
+    time_end(c);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    *done = true;
+    return VS_OK;
+}
+
 template <class F>
 static int launch_eval_t(vs_ctx *c, int k, bool heavy, const SourceDev &src, const ScaleDev &s, const F &f, uint64_t i_begin,
                          uint64_t i_end, double *fvals) {
@@ -117,6 +275,9 @@ int launch_eval_values(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s
     switch (o.id) {
     case VS_OBJ_GFUNCTION: {
         GFunction f{o.params + k, o.params + 2 * k};
+        bool done = false;
+        VS_TRY(launch_eval_pf(c, k, src, s, f, i_begin, i_end, fvals, &done));
+        if (done) return VS_OK;
         return launch_eval_t(c, k, false, src, s, f, i_begin, i_end, fvals);
     }
     case VS_OBJ_ISHIGAMI: {

@@ -52,6 +52,8 @@ struct HaltonDev {
     int mode;               // enum vs_halton_mode (HORNER: the table is not used)
     const double *fixed;    // the same terms in the fused kernels' fixed layout (all digit positions of a 32-bit index), k <= 32
     uint32_t fixed_len;
+    const double *arh, *arl; // [k][7] double-double reciprocals / 8 of the computed-term form (host.cu: build_arith), device
+    int arith_ok;           // they reproduce the term table bit for bit
 };
 
 // scale.py:33 / :62 lowered: linear  -> p * w + lb   (w = ub - lb rounded on the host, as numpy does)
@@ -123,6 +125,7 @@ struct Options {
     int halton_mode = 0;        // VS_HALTON_MODE    term-table arithmetic (enum vs_halton_mode)
     int index_bits = 0;         // VS_INDEX_BITS=32 forces the general (32-bit index) fused kernel
     int no_bulk_export = 0;     // VS_NO_BULK_EXPORT=1: export mode through the scalar-store kernel
+    int no_pf_eval = 0;         // VS_NO_PF_EVAL=1: two-phase path evaluates product-form functors point by point (old kernel)
 };
 
 // What the tail of the fused kernel has to do after the CTA partial sums are complete (host side of FusedTail).
