@@ -165,6 +165,9 @@ struct ExportGeom {
     uint64_t ntiles;
 };
 
+#ifndef EX_WAIT_HINT_NS
+#define EX_WAIT_HINT_NS 500u
+#endif
 __device__ __forceinline__ uint32_t ex_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ex_bar_init(uint64_t *b, uint32_t n) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ex_smem(b)), "r"(n) : "memory");
@@ -181,7 +184,7 @@ __device__ __forceinline__ void ex_bar_wait(uint64_t *b, uint32_t parity) {
         "@p bra D_%=;\n"
         "bra W_%=;\n"
         "D_%=:\n"
-        "}\n" ::"r"(ex_smem(b)), "r"(parity), "r"(0x989680u)
+        "}\n" ::"r"(ex_smem(b)), "r"(parity), "r"(EX_WAIT_HINT_NS)      // short suspend hint: the hand-over latency is on the tile's critical path
         : "memory");
 }
 __device__ __forceinline__ void ex_bulk_store(double *dst, const double *src_smem, uint32_t bytes) {
@@ -307,12 +310,20 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             }
             if (lane == 0) ex_bulk_store(out + orow * (uint64_t)k, buf + (size_t)r0 * k, (uint32_t)((r1 - r0) * k * 8));
         };
-        // does block t of this tile intersect the window?  (blocks outside it cost nothing: no patch, no fence, no wait)
-        auto wanted = [&](int t) {
-            if (g.mode != 0) return true;
-            const uint64_t R0 = (uint64_t)t * n + i0;
-            return !(R0 + rows <= g.row_begin || R0 >= g.row_end);
-        };
+        // blocks [t_min, t_max] of this tile intersect the window (R0(t) = t n + i0 is monotonic in t): two divisions per tile,
+        // then blocks outside cost one integer compare -- no patch, no fence, no wait
+        int t_min = 0, t_max = 2 * k + 1;
+        if (g.mode == 0) {
+            const uint64_t lo_num = g.row_begin > i0 + (uint64_t)rows - 1 ? g.row_begin - i0 - (uint64_t)rows + 1 : 0;   // t n > row_begin - i0 - rows
+            const uint64_t tm = (lo_num + n - 1) / n;
+            t_min = tm > (uint64_t)(2 * k + 2) ? 2 * k + 2 : (int)tm;
+            if (g.row_end <= i0) t_max = -1;
+            else {
+                const uint64_t tx = (g.row_end - 1 - i0) / n;
+                t_max = tx > (uint64_t)(2 * k + 1) ? 2 * k + 1 : (int)tx;
+            }
+        }
+        auto wanted = [&](int t) { return t >= t_min && t <= t_max; };
         int last = -1;                                          // tile of the most recent bulk group: 0 = A, 1 = B
         int pa_col = -1, pb_col = -1;                           // column currently patched in A / B
         double pa_val = 0.0, pb_val = 0.0;                      // ... and its original value (this lane's row)
