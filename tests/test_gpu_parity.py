@@ -283,6 +283,70 @@ def test_partials_tensor_path_matches_register_path(ctx, k, rows, monkeypatch):
         numpy.testing.assert_allclose(a[:4], [d[0].sum(), d[1].sum(), (d[0] ** 2).sum(), (d[1] ** 2).sum()], rtol=1e-11, atol=1e-9)
 
 
+@pytest.mark.parametrize("k,rows,l", [(6, 333, 1), (6, 1, 1), (20, 1031, 1), (50, 259, 1), (3, 70, 2), (6, 256, 3), (6, 257, 3),
+                                      (2, 3, 5), (10, 333, 3), (20, 515, 2), (4, 1001, 7), (30, 130, 2), (1, 65, 16),
+                                      (2, 37, 9), (1, 7, 1), (12, 4099, 3)])
+def test_partials_tensor_path_general_form(ctx, k, rows, l, monkeypatch):
+    """l > 1 outputs and odd row counts run the general form of the bulk-copy + DMMA kernel (one bulk copy per value block
+    and chunk, runs that start 8 bytes off a 16-byte boundary copied from one element earlier); VS_GRAM_GEN=0 forces the
+    register-tile kernel.  Same sufficient statistics (coordinate c = t*l + o), with and without the second-order block;
+    bit-reproducible."""
+    rng = numpy.random.RandomState(100 * k + rows + l)
+    nt = 2 + 2 * k
+    vals = rng.rand(nt * rows, l) * 2.0 + 5.0                              # Objective.flat(): row t*rows + r, column o
+    shift = vals[0].copy()
+    V = vals.reshape(nt, rows, l).transpose(0, 2, 1).reshape(nt * l, rows)   # coordinate-major
+    want = V @ V.T
+    m = nt * l
+    d = V[:2 * l] - numpy.concatenate([shift, shift])[:, None]
+    for flags in (vb_flags_second(), 0):
+        monkeypatch.delenv("VS_GRAM_GEN", raising=False)
+        ctx.reload_env()
+        a = ctx.partials_from_values(k, l, rows, vals, shift=shift, flags=flags)
+        a2 = ctx.partials_from_values(k, l, rows, vals, shift=shift, flags=flags)
+        assert (a == a2).all()
+        monkeypatch.setenv("VS_GRAM_DEBUG", "1")                            # elimination switch of the tensor-path kernel only:
+        ctx.reload_env()                                                    # no Gram update -> proves that kernel ran (no fallback)
+        z = ctx.partials_from_values(k, l, rows, vals, shift=shift, flags=flags)
+        monkeypatch.delenv("VS_GRAM_DEBUG", raising=False)
+        assert (z[4 * l:] == 0.0).all()
+        monkeypatch.setenv("VS_GRAM_GEN", "0")
+        ctx.reload_env()
+        b = ctx.partials_from_values(k, l, rows, vals, shift=shift, flags=flags)
+        monkeypatch.delenv("VS_GRAM_GEN", raising=False)
+        ctx.reload_env()
+        G = numpy.zeros((m, m))
+        G[numpy.triu_indices(m)] = a[4 * l:]
+        Gb = numpy.zeros((m, m))
+        Gb[numpy.triu_indices(m)] = b[4 * l:]
+        top = m if flags else 2 * l
+        numpy.testing.assert_allclose(G[:top], numpy.triu(want)[:top], rtol=1e-13)
+        numpy.testing.assert_allclose(G[:top], Gb[:top], rtol=1e-13)
+        sums = numpy.concatenate([d.sum(axis=1), (d ** 2).sum(axis=1)])
+        numpy.testing.assert_allclose(a[:4 * l], sums, rtol=1e-11, atol=1e-9)
+        numpy.testing.assert_allclose(a[:4 * l], b[:4 * l], rtol=1e-11, atol=1e-9)
+
+
+def test_partials_general_form_device_buffer_with_guards(ctx):
+    """The general form reads one element before / after a misaligned run: with the values in the MIDDLE of a device
+    allocation whose neighbours are NaN the result must not change (and nothing may be written around the outputs)."""
+    import torch
+    k, rows, l = 5, 77, 3
+    nt = 2 + 2 * k
+    rng = numpy.random.RandomState(9)
+    vals = rng.rand(nt * rows, l) + 1.0
+    host = ctx.partials_from_values(k, l, rows, vals, shift=vals[0])
+    pad = 64
+    buf = torch.full((vals.size + 2 * pad,), float("nan"), dtype=torch.float64, device="cuda")
+    buf[pad:pad + vals.size] = torch.from_numpy(vals.ravel()).cuda()
+    out = torch.full((host.size + 2 * pad,), float("nan"), dtype=torch.float64, device="cuda")
+    ctx.partials_from_values(k, l, rows, buf[pad:pad + vals.size], shift=vals[0], out=out[pad:pad + host.size])
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert (got[pad:pad + host.size] == host).all()
+    assert numpy.isnan(got[:pad]).all() and numpy.isnan(got[pad + host.size:]).all()
+
+
 def vb_flags_second():
     from varsens_b200 import _cabi
     return _cabi.FLAG_SECOND_ORDER

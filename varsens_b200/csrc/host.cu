@@ -68,6 +68,7 @@ void load_options(Options &o) {
     o.debug_skip = env_int("VS_DEBUG_SKIP", 0);
     if (const char *t = getenv("VS_TRACE")) o.trace = t;
     o.gram_mma = env_int("VS_GRAM_MMA", -1);
+    o.gram_mma_gen = env_int("VS_GRAM_GEN", -1);
     o.gram_st = env_int("VS_GRAM_ST", 0);
     o.gram_rc = env_int("VS_GRAM_RC", 0);
     o.gram_stages = env_int("VS_GRAM_STAGES", 0);

@@ -1,4 +1,4 @@
-// Estimator reductions on given values, tensor path (scalar objectives, l = 1).
+// Estimator reductions on given values, tensor path.
 //
 // Computes the same partial-sum vector as gram_kernel (kernels_vals.cu) -- the symmetric Gram
 // G = sum_i v_i v_i^T of the per-row vector v_i = (f(M_1[i]), f(M_2[i]), f(N_j[.][i]), f(N_nj[.][i])) plus the
@@ -13,6 +13,12 @@
 //     and loads conflict-free (pitch = 4 mod 16).  A warp owns one ST x ST super-tile of 8x8 blocks (its accumulators
 //     never leave registers) and a subset of the 4-row steps of every chunk.
 //   * row subsets, then CTAs, are combined in a fixed order -> bit-reproducible.
+//   * GEN form (l > 1 outputs, or an odd row count): block t of the value layout is a contiguous run of rows*l doubles
+//     fvals[(t*rows + r)*l + o], so a chunk of RC rows of block t is still ONE bulk copy of RC*l doubles into
+//     Yt[t][mis_t + r*l + o]; mis_t = 1 when the run starts 8 bytes off a 16-byte boundary (rows*l odd, t odd): the copy
+//     then starts one element early and is rounded up to 16 bytes (the neighbours it touches belong to the same
+//     array).  Coordinate c = t*l + o (the order of the partial-sum vector); each lane keeps the shared-memory offset of
+//     its coordinate of every block of its super-tile in registers, padded coordinates point at a zero row.
 //
 // Bound: max(HBM, FP64).  k = 20: 336 B and 21 DMMA (10.8 kflop) per row -> 0.22 ms of HBM and 0.30 ms of FP64 for
 // n = 2^22 on a B200.
@@ -28,6 +34,9 @@ namespace vs {
 
 struct MmaGeom {
     int m, nb, mpad;       // coordinates, 8-wide blocks, padded coordinates
+    int l, nt;             // outputs per evaluation, value blocks (2 + 2k); m = nt * l
+    int gen;               // GEN form (l > 1 or odd rows*l): per-lane coordinate offsets, see the header
+    int oddrun;            // rows * l is odd: the runs of odd blocks start 8 bytes off a 16-byte boundary
     int imax;              // block rows that are needed (nb, or 1 without the second-order block)
     int nsb, nunits;       // super-blocks per side, super-tiles in use
     int upc, passes;       // super-tiles per CTA, grid.y
@@ -93,22 +102,26 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 //   FULL : every row of the chunk is valid (all chunks but the last one) -> no per-lane row predicate.
 // Keep this loop lean: it issues next to the DMMAs (a first version that re-derived `valid` from the kernel arguments for
 // every predicated load ran 376 instructions per step and was issue-bound at 0.89 ms; see profiles/r01_gram_mma_ncu.txt).
-template <int ST, bool DIAG, bool GUARD, bool FULL>
-__device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double &sS, double &sQ, const double *__restrict__ Ya,
-                                          const double *__restrict__ Yb, int colstride, int valid, int rsub, int rs, int lane,
-                                          int xmax, int ymax, int share, bool do_sums, double shiftv) {
+//   GEN  : l > 1 or odd rows: the fragment of block x is at Ya[offa[x] + r0 * l] (offa, offb: per-lane register tables) and
+//          the shifted sums cover the coordinates c < 2l of the diagonal super-tile (sS, sQ: one pair per block).
+template <int ST, bool DIAG, bool GUARD, bool FULL, bool GEN>
+__device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double (&sS)[GEN ? ST : 1], double (&sQ)[GEN ? ST : 1],
+                                          const double *__restrict__ Ya, const double *__restrict__ Yb, int colstride, int valid,
+                                          int rsub, int rs, int lane, int xmax, int ymax, int share, bool do_sums,
+                                          const double (&shiftv)[GEN ? ST : 1], const int (&offa)[GEN ? ST : 1],
+                                          const int (&offb)[GEN ? ST : 1], int l, unsigned summask) {
     const int ksteps = (valid + 3) >> 2;
     const int lrow = lane & 3;
 #pragma unroll 1
     for (int ks = rsub; ks < ksteps; ks += rs) {
-        const int r0 = ks << 2;
-        const bool rv = FULL || (r0 + lrow < valid);
+        const int r0 = GEN ? (ks << 2) * l : (ks << 2);          // element offset of the step's first row inside a run
+        const bool rv = FULL || ((ks << 2) + lrow < valid);
         double fa[ST], fb[ST];
 #pragma unroll
         for (int x = 0; x < ST; ++x) {
             const bool on = (!GUARD || x < xmax) && rv;
             fa[x] = 0.0;
-            if (on) fa[x] = Ya[x * colstride + r0];
+            if (on) fa[x] = GEN ? Ya[offa[x] + r0] : Ya[x * colstride + r0];
         }
         if (DIAG && (!GUARD || share)) {
 #pragma unroll
@@ -119,13 +132,23 @@ __device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double &sS,
             for (int y = 0; y < ST; ++y) {
                 const bool on = (!GUARD || y < ymax) && rv;
                 fb[y] = 0.0;
-                if (on) fb[y] = Yb[y * colstride + r0];
+                if (on) fb[y] = GEN ? Yb[offb[y] + r0] : Yb[y * colstride + r0];
             }
         }
         if (DIAG && do_sums) {
-            const double d = rv ? fa[0] - shiftv : 0.0;      // lanes 0-3: f(M_1) rows, lanes 4-7: f(M_2) rows
-            sS += d;
-            sQ = fma(d, d, sQ);
+            if constexpr (!GEN) {
+                const double d = rv ? fa[0] - shiftv[0] : 0.0;      // lanes 0-3: f(M_1) rows, lanes 4-7: f(M_2) rows
+                sS[0] += d;
+                sQ[0] = fma(d, d, sQ[0]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < ST; ++x)
+                    if (summask >> x & 1u) {                         // this lane's coordinate of block x is one of the 2l summed ones
+                        const double d = rv ? fa[x] - shiftv[x] : 0.0;
+                        sS[x] += d;
+                        sQ[x] = fma(d, d, sQ[x]);
+                    }
+            }
         }
 #pragma unroll
         for (int x = 0; x < ST; ++x)
@@ -138,7 +161,7 @@ __device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double &sS,
 constexpr int MMA_BAR_DOUBLES = 16;     // full[8] + empty[8]
 constexpr int MMA_MAX_STAGES = 8;
 
-template <int ST, bool MULTI, bool GUARD>        // MULTI: several super-tiles (ST = 4); otherwise one diagonal super-tile
+template <int ST, bool MULTI, bool GUARD, bool GEN>   // MULTI: several super-tiles (ST = 4 or 2); otherwise one diagonal super-tile
 __global__ void __launch_bounds__(MULTI ? 512 : 384)
 gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, const double *__restrict__ shift,
                 double *__restrict__ blockpart) {
@@ -148,7 +171,9 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
     double *stages = smem + MMA_BAR_DOUBLES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = g.warps;
-    const int stage_elems = g.mpad * g.pitch;
+    // staged rows per stage: the mpad padded coordinates, or (GEN) the nt value blocks plus one zero row for the padding
+    const int stage_rows = GEN ? g.nt + 1 : g.mpad;
+    const int stage_elems = stage_rows * g.pitch;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.nstage; ++s) {
@@ -157,10 +182,11 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // the padded coordinates m .. mpad-1 are never copied: zero them once
-    for (int e = threadIdx.x; e < g.nstage * (g.mpad - g.m) * g.pitch; e += blockDim.x) {
-        const int s = e / ((g.mpad - g.m) * g.pitch), rem = e - s * ((g.mpad - g.m) * g.pitch);
-        stages[(size_t)s * stage_elems + (size_t)g.m * g.pitch + rem] = 0.0;
+    // the padded coordinates m .. mpad-1 (GEN: the zero row) are never copied: zero them once
+    const int zrow0 = GEN ? g.nt : g.m, zrows = stage_rows - zrow0;
+    for (int e = threadIdx.x; e < g.nstage * zrows * g.pitch; e += blockDim.x) {
+        const int s = e / (zrows * g.pitch), rem = e - s * (zrows * g.pitch);
+        stages[(size_t)s * stage_elems + (size_t)zrow0 * g.pitch + rem] = 0.0;
     }
     __syncthreads();
 
@@ -171,7 +197,10 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
     double acc[ST * ST][2];
 #pragma unroll
     for (int t = 0; t < ST * ST; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    double sS = 0.0, sQ = 0.0;
+    constexpr int NS = GEN ? ST : 1;
+    double sS[NS], sQ[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) { sS[x] = 0.0; sQ[x] = 0.0; }
 
     // work item of this warp: the host spreads the super-tiles over the four sub-partitions by DMMA count (the FP64 pipe is
     // per sub-partition, and a diagonal or edge super-tile has far fewer 8x8 tiles than an interior one)
@@ -196,11 +225,26 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
             if (g.debug == 2) {
                 if (lane == 0) bar_arrive(full + s);
             } else if (elect_one()) {
-                bar_arrive_expect(full + s, (uint32_t)g.m * valid * 8u);
                 double *dst = stages + (size_t)s * stage_elems;
-                const double *src = fvals + r0;
+                if constexpr (!GEN) {
+                    bar_arrive_expect(full + s, (uint32_t)g.m * valid * 8u);
+                    const double *src = fvals + r0;
 #pragma unroll 4
-                for (int t = 0; t < g.m; ++t) bulk_g2s(dst + (size_t)t * g.pitch, src + (uint64_t)t * rows, valid * 8u, full + s);
+                    for (int t = 0; t < g.m; ++t) bulk_g2s(dst + (size_t)t * g.pitch, src + (uint64_t)t * rows, valid * 8u, full + s);
+                } else {
+                    // run of block t: valid*l doubles from fvals[(t*rows + r0)*l]; even blocks start on a 16-byte boundary, odd
+                    // blocks too unless rows*l is odd -- then they start one element early.  Sizes rounded up to 16 bytes.
+                    const uint32_t nel = valid * (uint32_t)g.l;
+                    const uint32_t be = ((nel + 1u) & ~1u) * 8u, bo = ((nel + (uint32_t)g.oddrun + 1u) & ~1u) * 8u;
+                    bar_arrive_expect(full + s, (uint32_t)(g.nt / 2) * (be + bo));
+                    const double *src = fvals + r0 * (uint64_t)g.l;
+                    const uint64_t run = rows * (uint64_t)g.l;
+#pragma unroll 2
+                    for (int t = 0; t < g.nt; t += 2) {
+                        bulk_g2s(dst + (size_t)t * g.pitch, src + (uint64_t)t * run, be, full + s);
+                        bulk_g2s(dst + (size_t)(t + 1) * g.pitch, src + (uint64_t)(t + 1) * run - g.oddrun, bo, full + s);
+                    }
+                }
             }
             __syncwarp();
             if (++s == g.nstage) { s = 0; par ^= 1u; }
@@ -209,10 +253,36 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
         // ------------------------------------ consumers -----------------------------------
         const int foff = (lane >> 2) * g.pitch + (lane & 3);
         const bool do_sums = active && u == g.sumu;
-        const double shiftv = shift ? *shift : 0.0;
         const int colstride = 8 * g.pitch;
         const int xmax = g.imax - ST * I, ymax = g.nb - ST * J;   // blocks of this super-tile that exist (row / column side)
-        const double *Ya0 = stages + foff + (ST * I) * colstride, *Yb0 = stages + foff + (ST * J) * colstride;
+        const double *Ya0 = stages + (GEN ? 0 : foff + (ST * I) * colstride), *Yb0 = stages + (GEN ? 0 : foff + (ST * J) * colstride);
+        // GEN: shared-memory offset of this lane's coordinate c = 8*block + lane/4 at row lane%4 of a chunk, for every block of
+        // the super-tile: value block t = c / l (row t of the stage, shifted by one element when its run is misaligned),
+        // output o = c % l, row stride l.  Coordinates >= m read the zero row.
+        int offa[NS], offb[NS];
+        double shiftv[NS];
+        unsigned summask = 0;
+#pragma unroll
+        for (int x = 0; x < NS; ++x) { offa[x] = 0; offb[x] = 0; shiftv[x] = 0.0; }
+        if constexpr (GEN) {
+            auto off_of = [&](int c) {
+                if (c >= g.m) return g.nt * g.pitch + (lane & 3) * g.l;
+                const int t = c / g.l, o = c - t * g.l;
+                return t * g.pitch + ((t & 1) ? g.oddrun : 0) + o + (lane & 3) * g.l;
+            };
+#pragma unroll
+            for (int x = 0; x < ST; ++x) {
+                const int ca = 8 * (ST * I + x) + (lane >> 2), cb = 8 * (ST * J + x) + (lane >> 2);
+                offa[x] = off_of(ca);
+                offb[x] = off_of(cb);
+                if (do_sums && ca < 2 * g.l) {
+                    summask |= 1u << x;
+                    shiftv[x] = shift ? shift[ca % g.l] : 0.0;
+                }
+            }
+        } else {
+            shiftv[0] = shift ? *shift : 0.0;
+        }
         int s = 0;
         uint32_t par = 0;
         uint32_t ch = blockIdx.x;
@@ -223,8 +293,8 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
                 const bool fullc = ch + 1 != nchunks || last_valid == g.rc;
                 auto run = [&](auto diag, auto guard) {
                     constexpr bool D = decltype(diag)::value, G = decltype(guard)::value;
-                    if (fullc) mma_steps<ST, D, G, true>(acc, sS, sQ, Ya, Yb, colstride, g.rc, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv);
-                    else mma_steps<ST, D, G, false>(acc, sS, sQ, Ya, Yb, colstride, last_valid, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv);
+                    if (fullc) mma_steps<ST, D, G, true, GEN>(acc, sS, sQ, Ya, Yb, colstride, g.rc, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv, offa, offb, g.l, summask);
+                    else mma_steps<ST, D, G, false, GEN>(acc, sS, sQ, Ya, Yb, colstride, last_valid, rsub, g.rs, lane, xmax, ymax, g.second, D && do_sums, shiftv, offa, offb, g.l, summask);
                 };
                 using T_ = std::true_type;
                 using F_ = std::false_type;
@@ -246,7 +316,7 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
     __syncthreads();
     constexpr int SD = 8 * ST;                                  // super-tile side in coordinates
     double *img = stages;                                       // [upc][SD][SD]
-    double *sums = img + (size_t)g.upc * SD * SD;               // [rs][8][2]
+    double *sums = img + (size_t)g.upc * SD * SD;               // [rs][NS][32][2]: (block, lane) = (coordinate, row mod 4)
     for (int round = 0; round < g.rs; ++round) {
         if (active && rsub == round) {
             double *mine = img + (size_t)ul * SD * SD;
@@ -259,14 +329,17 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
                     if (round == 0) { dst[0] = acc[x * ST + y][0]; dst[1] = acc[x * ST + y][1]; }
                     else { dst[0] += acc[x * ST + y][0]; dst[1] += acc[x * ST + y][1]; }
                 }
-            if (u == g.sumu && lane < 8) {
-                sums[(round * 8 + lane) * 2 + 0] = sS;
-                sums[(round * 8 + lane) * 2 + 1] = sQ;
+            if (u == g.sumu) {
+#pragma unroll
+                for (int x = 0; x < NS; ++x) {
+                    sums[((round * NS + x) * 32 + lane) * 2 + 0] = sS[x];
+                    sums[((round * NS + x) * 32 + lane) * 2 + 1] = sQ[x];
+                }
             }
         }
         __syncthreads();
     }
-    const size_t per_block = (size_t)g.mpad * g.mpad + 4;
+    const size_t per_block = (size_t)g.mpad * g.mpad + 4 * (size_t)g.l;
     double *bp = blockpart + (size_t)blockIdx.x * per_block;
     for (int q = 0; q < g.upc; ++q) {
         const int uq = blockIdx.y * g.upc + q;
@@ -278,33 +351,34 @@ gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, cons
             if (gp < g.mpad && gq < g.mpad) bp[(size_t)gp * g.mpad + gq] = img[(size_t)q * SD * SD + e];
         }
     }
-    if ((int)blockIdx.y == g.sumu / g.upc && threadIdx.x < 4) {
-        // S_A, S_B, Q_A, Q_B: subsets in order, lanes in order
-        const int col = threadIdx.x & 1, which = threadIdx.x >> 1;
+    if ((int)blockIdx.y == g.sumu / g.upc && (int)threadIdx.x < 4 * g.l) {
+        // S_A[l], S_B[l], Q_A[l], Q_B[l] (coordinate c = t*l + o, t in {0, 1}): subsets in order, the four row lanes in order
+        const int c = threadIdx.x % (2 * g.l), which = threadIdx.x / (2 * g.l);
+        const int x = GEN ? c >> 3 : 0, cl = c & 7;
         double s = 0.0;
         for (int round = 0; round < g.rs; ++round)
-            for (int ln = 0; ln < 4; ++ln) s += sums[(round * 8 + col * 4 + ln) * 2 + which];
+            for (int ln = 0; ln < 4; ++ln) s += sums[((round * NS + x) * 32 + cl * 4 + ln) * 2 + which];
         bp[(size_t)g.mpad * g.mpad + threadIdx.x] = s;
     }
 }
 
-// per-CTA dense images (mpad x mpad + 4 sums) -> packed partial-sum vector; entries that were not computed are 0.
+// per-CTA dense images (mpad x mpad + 4l sums) -> packed partial-sum vector; entries that were not computed are 0.
 // One warp per entry: lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree (reproducible for a given grid).
-__global__ void __launch_bounds__(256) gram_mma_scatter_kernel(int m, int mpad, int pmax, int nblocks, const double *__restrict__ blockpart,
+__global__ void __launch_bounds__(256) gram_mma_scatter_kernel(int m, int mpad, int l, int pmax, int nblocks, const double *__restrict__ blockpart,
                                                                double *__restrict__ partials) {
-    const size_t per_block = (size_t)mpad * mpad + 4;
+    const size_t per_block = (size_t)mpad * mpad + 4 * (size_t)l;
     const int lane = threadIdx.x & 31;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nent = (long long)m * (m + 1) / 2;
-    if (w >= nent + 4) return;
+    if (w >= nent + 4 * l) return;
     const double *src;
     long long dst;
     bool computed = true;
-    if (w < 4) {
+    if (w < 4 * l) {
         src = blockpart + (size_t)mpad * mpad + w;
         dst = w;
     } else {
-        long long rem = w - 4;
+        long long rem = w - 4 * l;
         int p = 0, rowlen = m;
         while (rem >= rowlen) { rem -= rowlen; --rowlen; ++p; }
         const int q = p + (int)rem;
@@ -319,10 +393,10 @@ __global__ void __launch_bounds__(256) gram_mma_scatter_kernel(int m, int mpad, 
     if (lane == 0) partials[dst] = s;
 }
 
-template <int ST, bool MULTI, bool GUARD>
+template <int ST, bool MULTI, bool GUARD, bool GEN>
 static int launch_mma_t(vs_ctx *c, const MmaGeom &g, size_t smem, uint64_t rows, const double *fvals, const double *shift_dev,
                         double *partials) {
-    auto kern = gram_mma_kernel<ST, MULTI, GUARD>;
+    auto kern = gram_mma_kernel<ST, MULTI, GUARD, GEN>;
     VS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = (g.warps + 1) * 32;
     int occ = 1;
@@ -332,14 +406,15 @@ static int launch_mma_t(vs_ctx *c, const MmaGeom &g, size_t smem, uint64_t rows,
     const uint64_t nchunks = (rows + g.rc - 1) / g.rc;
     int gx = (int)(nchunks < (uint64_t)occ * c->sm_count ? nchunks : (uint64_t)occ * c->sm_count);
     if (gx < 1) gx = 1;
-    const size_t per_block = (size_t)g.mpad * g.mpad + 4;
+    const size_t per_block = (size_t)g.mpad * g.mpad + 4 * (size_t)g.l;
     VS_TRY(ensure(c, c->block_buf, (size_t)gx * per_block * sizeof(double)));
     time_begin(c);
     kern<<<dim3(gx, g.passes), threads, smem, c->stream>>>(g, rows, fvals, shift_dev, (double *)c->block_buf.p);
     time_end(c);
     c->launches++;
     VS_CUDA(cudaGetLastError());
-    gram_mma_scatter_kernel<<<(unsigned)(((size_t)g.m * (g.m + 1) / 2 + 4 + 7) / 8), 256, 0, c->stream>>>(g.m, g.mpad, g.second ? g.m : 8, gx,
+    // (without the second-order block only the block rows holding f(M_1), f(M_2) -- coordinates < 2l -- exist in the image)
+    gram_mma_scatter_kernel<<<(unsigned)(((size_t)g.m * (g.m + 1) / 2 + 4 * g.l + 7) / 8), 256, 0, c->stream>>>(g.m, g.mpad, g.l, g.second ? g.m : 8 * g.imax, gx,
                                                                                  (const double *)c->block_buf.p, partials);
     c->launches++;
     VS_CUDA(cudaGetLastError());
@@ -350,15 +425,20 @@ static int launch_mma_t(vs_ctx *c, const MmaGeom &g, size_t smem, uint64_t rows,
 int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev, int flags,
                     double *partials, bool *handled) {
     *handled = false;
-    if (l != 1 || (rows & 1) || (reinterpret_cast<uintptr_t>(fvals) & 15) || rows == 0) return VS_OK;
+    if ((reinterpret_cast<uintptr_t>(fvals) & 15) || rows == 0 || l < 1) return VS_OK;
     if (c->opt.gram_mma == 0) return VS_OK;
     MmaGeom g{};
-    g.m = 2 + 2 * k;
+    g.l = l;
+    g.nt = 2 + 2 * k;
+    g.m = g.nt * l;
+    g.oddrun = (int)((rows & 1) && (l & 1));                 // rows * l odd: odd value blocks start 8 bytes off a 16-byte boundary
+    g.gen = (l != 1 || (rows & 1)) ? 1 : 0;
+    if (g.gen && c->opt.gram_mma_gen == 0) return VS_OK;     // VS_GRAM_GEN=0: register-tile kernel for l > 1 / odd rows
     g.nb = (g.m + 7) / 8;
     g.mpad = 8 * g.nb;
     g.second = (flags & VS_FLAG_SECOND_ORDER) ? 1 : 0;
-    g.imax = g.second ? g.nb : 1;
-    if (rows >= (1ull << 36)) return VS_OK;
+    g.imax = g.second ? g.nb : (2 * l + 7) / 8;              // first order only: the rows of f(M_1), f(M_2) (coordinates < 2l)
+    if (rows >= (1ull << 36) / (uint64_t)l) return VS_OK;
     // One diagonal super-tile of side ST >= nb when the whole matrix fits one warp's accumulators (k <= 23); otherwise
     // ST x ST super-tiles, ST in {4, 2} picked by a cost model fitted to B200 measurements (profiles/r01_gram_mma.txt):
     // a warp retires one DMMA per 60-80 cycles whatever else runs, so a pass costs (8x8 tiles of the heaviest super-tile /
@@ -380,6 +460,8 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
         if (best == 0.0) return VS_OK;            // more super-tiles than the tables hold: register-tile kernel
     }
     if (multi && (c->opt.gram_st == 2 || c->opt.gram_st == 4)) ST = c->opt.gram_st;                  // tuning switch (VS_GRAM_ST)
+    if (multi && 2 * l > 8 * ST) ST = 4;                      // the shifted sums (coordinates < 2l) live in super-tile (0, 0)
+    if (2 * l > 8 * ST) return VS_OK;
     const bool guard = multi || !g.second || g.nb != ST;
     g.nsb = (g.nb + ST - 1) / ST;
     g.nunits = g.second ? g.nsb * (g.nsb + 1) / 2 : g.nsb;
@@ -425,21 +507,25 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
         }
     }
     const size_t avail = c->smem_optin;                       // 227 KB on sm_100a
-    const size_t tail = ((size_t)g.upc * (8 * ST) * (8 * ST) + (size_t)g.rs * 16) * sizeof(double);
+    const size_t tail = ((size_t)g.upc * (8 * ST) * (8 * ST) + (size_t)g.rs * (g.gen ? ST : 1) * 64) * sizeof(double);
     // rows per chunk: as large as a ~60 KB stage allows (fewer, larger bulk copies and barrier round trips), ring of 3-6 stages
     int rc_cap = 256;
     if (c->opt.gram_rc > 0) rc_cap = c->opt.gram_rc;                                          // tuning switch (VS_GRAM_RC)
     size_t smem = 0;
     g.nstage = 0;
-    for (int rc : {256, 128, 64, 32}) {
+    for (int rc : {256, 128, 64, 32, 16, 8}) {
         if (rc > rc_cap && rc > 32) continue;
-        const size_t stage = (size_t)g.mpad * (rc + 4) * sizeof(double);
+        if (rc < 32 && !g.gen) break;
+        // doubles per staged row: rc (GEN: rc * l, + 2 for a misaligned start and the 16-byte round-up), pitch = 4 mod 16
+        const int need = g.gen ? rc * l + 2 : rc;
+        const int pitch = ((need + 11) / 16) * 16 + 4;
+        const size_t stage = (size_t)(g.gen ? g.nt + 1 : g.mpad) * pitch * sizeof(double);
         int ns = (int)((avail - 2048) / stage);                 // one CTA per SM: the ring is what keeps HBM busy
         if (ns > 6) ns = 6;
-        if ((stage > 60 * 1024 || ns < 3) && rc > 32) continue;
+        if ((stage > 60 * 1024 || ns < 3) && rc > (g.gen ? 8 : 32)) continue;
         if (ns < 2) break;
         g.rc = rc;
-        g.pitch = rc + 4;
+        g.pitch = pitch;
         g.nstage = ns;
         smem = MMA_BAR_DOUBLES * sizeof(double) + (size_t)ns * stage;
         break;
@@ -451,7 +537,9 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
     if (smem < MMA_BAR_DOUBLES * sizeof(double) + tail) smem = MMA_BAR_DOUBLES * sizeof(double) + tail;
     if (smem > avail) return VS_OK;
     int rc = VS_OK;
-#define VS_MMA_CASE(S, M, G) rc = launch_mma_t<S, M, G>(c, g, smem, rows, fvals, shift_dev, partials)
+#define VS_MMA_CASE(S, M, G)                                                                       \
+    rc = g.gen ? launch_mma_t<S, M, G, true>(c, g, smem, rows, fvals, shift_dev, partials)         \
+               : launch_mma_t<S, M, G, false>(c, g, smem, rows, fvals, shift_dev, partials)
     if (multi) { if (ST == 4) VS_MMA_CASE(4, true, true); else VS_MMA_CASE(2, true, true); }
     else if (ST == 2) { if (guard) VS_MMA_CASE(2, false, true); else VS_MMA_CASE(2, false, false); }
     else if (ST == 3) { if (guard) VS_MMA_CASE(3, false, true); else VS_MMA_CASE(3, false, false); }

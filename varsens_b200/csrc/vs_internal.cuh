@@ -120,6 +120,7 @@ struct Options {
     int debug_skip = 0;         // VS_DEBUG_SKIP
     std::string trace;          // VS_TRACE          file for CTA 0's clock stamps
     int gram_mma = -1;          // VS_GRAM_MMA       (-1 = default)
+    int gram_mma_gen = -1;      // VS_GRAM_GEN       0: register-tile kernel for l > 1 outputs / odd row counts
     int gram_st = 0, gram_rc = 0, gram_stages = 0, gram_hint = 0x989680, gram_debug = 0;
     int p2p_timeout_ms = 10000; // VS_P2P_TIMEOUT_MS bounded wait for the peers' flags in the exchange
     int halton_mode = 0;        // VS_HALTON_MODE    term-table arithmetic (enum vs_halton_mode)
@@ -200,7 +201,7 @@ size_t result_len(int k, int l);
 int launch_p2p_reduce_finalize(vs_ctx *c, int k, int l, uint64_t n, uint64_t rows, int world, int rank, const uint64_t *peer_bufs_dev,
                                const uint64_t *peer_flags_dev, uint32_t epoch, const double *partials, int flags, double *res_dev);
 int launch_gram_scatter(vs_ctx *c, const GramGeom &g, int nblocks, const double *blockpart, double *partials, int plen);
-// kernels_gram_mma.cu: tensor-path Gram for l == 1 (*handled = false -> caller falls back to gram_kernel)
+// kernels_gram_mma.cu: tensor-path Gram (*handled = false -> caller falls back to gram_kernel)
 int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals, const double *shift_dev, int flags,
                     double *partials, bool *handled);
 // kernels_fused.cu
