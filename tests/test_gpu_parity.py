@@ -190,6 +190,55 @@ def test_sample_flat_shard_and_bulk_kernel(ctx, k, n, discard, monkeypatch):
         assert (out.cpu().numpy() == blocks[:, :hi, :]).all()
 
 
+@pytest.mark.parametrize("env", [{}, {"VS_EXPORT_COPIES": "1"}, {"VS_EXPORT_COPIES": "2"}, {"VS_EXPORT_SLOW_GEN": "1"},
+                                 {"VS_HALTON_MODE": "1"}])
+def test_sample_flat_bulk_kernel_forms_and_guards(ctx, env, monkeypatch):
+    """Every form of the bulk export kernel -- one or two store warps (tile copies), the multiply-only digit loop with
+    computed terms and the generic loop, another term-table mode -- is bit-identical to the oracle for windows of every
+    shape (inside one block, across the M_1/M_2/N_j/N_nj boundaries, longer than k blocks, ragged last tile), and writes
+    nothing outside the window (NaN guard regions around the device output: compute-sanitizer is closed on this pool)."""
+    import torch
+    from varsens_b200 import _cabi
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    ctx.reload_env()
+    if "VS_HALTON_MODE" in env:
+        ctx.set_halton_mode(int(env["VS_HALTON_MODE"]))
+    try:
+        for k, n, discard in ((50, 333, 3), (12, 1000, 0), (4, 97, 0)):
+            mode = {"1": "reciprocal"}.get(env.get("VS_HALTON_MODE"), "divide")
+            if mode == "divide":
+                whole = cport.sample_flat(k, n, discard)
+            else:       # the oracle's restatement of that arithmetic as the unscaled points (Sample(raw=...) semantics)
+                whole = cport.sample_flat(k, n, discard, raw=ohalton.halton_points_mode(k, 20 * k + discard + 1, 2 * n, mode))
+            total = 2 * n * (1 + k)
+            pd = torch.from_numpy(perm_of(n).astype(numpy.int32)).cuda()
+            pad = 64
+            wins = [(0, total), (5, n - 3), (n - 1, n + 1), (2 * n + 11, 2 * n + 3 * n + 5), ((k + 1) * n + 7, (k + 3) * n + 9),
+                    (n + 1, (k + 4) * n - 2), (total - 33, total), (2 * n + (k - 1) * n - 5, 2 * n + k * n + 40)]
+            for lo, hi in wins:
+                buf = torch.full(((hi - lo) * k + 2 * pad,), float("nan"), dtype=torch.float64, device="cuda")
+                ctx.sample_flat(k, n, pd, discard, row_begin=lo, row_end=hi, out=buf[pad:pad + (hi - lo) * k].view(hi - lo, k))
+                ctx.synchronize()
+                got = buf.cpu().numpy()
+                assert (got[pad:-pad].reshape(hi - lo, k) == whole[lo:hi]).all(), (k, n, lo, hi)
+                assert numpy.isnan(got[:pad]).all() and numpy.isnan(got[-pad:]).all(), (k, n, lo, hi)
+            blocks = whole.reshape(2 + 2 * k, n, k)
+            for lo, hi in ((0, n), (n // 2, n // 2 + 45), (n - 1, n)):
+                sz = (2 + 2 * k) * (hi - lo) * k
+                buf = torch.full((sz + 2 * pad,), float("nan"), dtype=torch.float64, device="cuda")
+                ctx.sample_flat_shard(k, n, pd, lo, hi, discard, out=buf[pad:pad + sz].view(2 + 2 * k, hi - lo, k))
+                ctx.synchronize()
+                got = buf.cpu().numpy()
+                assert (got[pad:-pad].reshape(2 + 2 * k, hi - lo, k) == blocks[:, lo:hi, :]).all(), (k, n, lo, hi)
+                assert numpy.isnan(got[:pad]).all() and numpy.isnan(got[-pad:]).all()
+    finally:
+        for key in env:
+            monkeypatch.delenv(key, raising=False)
+        ctx.reload_env()
+        ctx.set_halton_mode(0)
+
+
 def test_sample_flat_large_property(ctx):
     """Structure at a size the oracle cannot hold (k=50, n=2^16 -> 2.7 GB on device): column-substitution
     identities of saltelli.py:119-123 checked on the device with torch, plus a checksum of checksums."""

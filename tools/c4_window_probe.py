@@ -17,3 +17,13 @@ ts = []
 for _ in range(4):
     ctx.sample_flat(k, n, p, row_begin=n - 1, row_end=n + 1, out=small); torch.cuda.synchronize(); ts.append(ctx.last_kernel_ms())
 print("generation of all n base rows (2-row window across a block boundary): kernel_ms", [round(t, 3) for t in ts])
+# small windows (the torch-objective route materialises 256 MB windows: Objective._evaluate_vectorized)
+for nbytes in (1 << 28, 1 << 30, 4 << 30):
+    rows = nbytes // (k * 8)
+    w = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+    for r0 in (0, 3 * n + 1001):
+        ts = []
+        for _ in range(4):
+            ctx.sample_flat(k, n, p, row_begin=r0, row_end=r0 + rows, out=w); torch.cuda.synchronize(); ts.append(ctx.last_kernel_ms())
+        print("window %5d MB r0=%d kernel_ms %.3f -> %.0f GB/s" % (nbytes >> 20, r0, min(ts[1:]), nbytes / (min(ts[1:]) * 1e-3) / 1e9))
+    del w

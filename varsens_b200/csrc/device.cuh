@@ -47,6 +47,72 @@ __device__ __forceinline__ double halton_coord(const HaltonDev &h, int d, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multiply-only digit loop for kernels with RUN-TIME bases (export mode, product-form evaluation): lane = base row, the
+// whole warp walks one dimension, the A chain and the B chain of a row advance together.  Per dimension (warp-uniform):
+//   nd  digit positions of the launch's largest index (an exhausted index keeps adding the term of digit 0 = 0.0: exact),
+//       so the loop has a fixed trip count -- no per-step "any lane left?" test, nothing for the compiler to predicate;
+//   jg  leading positions that need the general division (64-bit magic mul-high), until m * 8b < 2^32 holds for every
+//       index of the launch; from there on  w = m * ceil(2^32 / b):  quotient = hi(w),  8 * digit = umulhi(lo(w), 8b)
+//       (two multiplies; proof and brute-force check: tools/check_fastdiv.py, the same step as fused_impl.cuh: digit_step).
+// The term of a digit is read from the shared-memory table (TABLE: row address + 8 * digit is the byte address), or
+// computed as fma(dd, rh, dd * rl), dd = 8 * digit -- the product with a double-double reciprocal, bit-equal to the table
+// entry (host.cu: build_arith checks every digit of every position and clears arith_ok otherwise).
+// ---------------------------------------------------------------------------------------------
+struct DimLoop {
+    uint32_t b8, c32;
+    int nd, jg;
+};
+
+__device__ __forceinline__ DimLoop dim_loop(uint32_t b, uint64_t max_index) {
+    DimLoop dl;
+    dl.b8 = 8u * b;
+    dl.c32 = (uint32_t)((0x100000000ull + b - 1) / b);
+    dl.nd = 0;
+    dl.jg = 0;
+    for (uint64_t m = max_index; m > 0; m /= b) {
+        if (m * 8ull * b >= 0x100000000ull) dl.jg = dl.nd + 1;
+        ++dl.nd;
+    }
+    return dl;
+}
+
+template <bool TABLE>
+__device__ __forceinline__ void halton_pair(uint32_t ma, uint32_t mb, uint32_t b, uint64_t magic, const DimLoop dl, uint32_t row,
+                                            const double *__restrict__ rh, const double *__restrict__ rl, double &pa, double &pb) {
+    auto term = [&](uint32_t off8, int j) -> double {
+        if constexpr (TABLE) {
+            double t;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(row + off8));
+            return t;
+        } else {
+            const double dd = __dadd_rn(__hiloint2double(0x43300000, (int)off8), -4503599627370496.0);   // 2^52 + off8, exact
+            return __fma_rn(dd, rh[j], __dmul_rn(dd, rl[j]));
+        }
+    };
+    pa = 0.0;
+    pb = 0.0;
+    int j = 0;
+#pragma unroll 1
+    for (; j < dl.jg; ++j) {                                  // usually 0 or 1 trips
+        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
+        pa = __dadd_rn(pa, term(8u * (ma - qa * b), j));
+        pb = __dadd_rn(pb, term(8u * (mb - qb * b), j));
+        ma = qa;
+        mb = qb;
+        if constexpr (TABLE) row += dl.b8;
+    }
+#pragma unroll 2
+    for (; j < dl.nd; ++j) {
+        const uint64_t wa = (uint64_t)ma * dl.c32, wb = (uint64_t)mb * dl.c32;
+        ma = (uint32_t)(wa >> 32);
+        mb = (uint32_t)(wb >> 32);
+        pa = __dadd_rn(pa, term(__umulhi((uint32_t)wa, dl.b8), j));
+        pb = __dadd_rn(pb, term(__umulhi((uint32_t)wb, dl.b8), j));
+        if constexpr (TABLE) row += dl.b8;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // scale.py:33 (two roundings: multiply, then add -- never an FMA) and :62.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double apply_scale(const ScaleDev &s, int d, double p) {

@@ -1,5 +1,7 @@
 // Generators and export-mode sample assembly.
 #include "device.cuh"
+#include <vector>
+#include <cstdio>
 
 namespace vs {
 
@@ -143,27 +145,44 @@ sample_flat_kernel(int k, int TI, SourceDev src, ScaleDev s, uint64_t i_lo, uint
 
 // ---------------------------------------------------------------------------------------------
 // K3, bulk form (even k, 16-byte aligned output): persistent CTAs, warp-specialised.
-//   warps 1..7  GENERATE the tile of TI base rows: A (M_1 rows) and B (shuffled M_2 rows), 2*TI*k radical inverses with the
-//               term table, the bases and the division magics in shared memory (the old kernel went to global memory for every
-//               digit), into one of two tile buffers -- the next tile is generated while the current one is being stored;
-//   warp 0      STORES the 2+2k flat blocks of the tile with the TMA: a block of the flat layout is the tile with ONE column
+//   14 warps    GENERATE the tile of TI = 32 base rows: A (M_1 rows) and B (shuffled M_2 rows), 2*TI*k radical inverses, into
+//               one of two tile-buffer pairs -- the next tile is generated while the current one is being stored.  lane = row,
+//               the warp walks one dimension at a time with the multiply-only digit loop of device.cuh (halton_pair): table
+//               terms from shared memory for bases < 37, computed terms (double-double reciprocal) for the rest, so the
+//               shared-memory table is 21 KB instead of 161 KB at k = 50.
+//   1-2 warps   STORE the 2+2k flat blocks of the tile with the TMA: a block of the flat layout is the tile with ONE column
 //               replaced, so the warp patches that column in place (lane = row: TI shared stores), issues one
 //               cp.async.bulk.global.shared::cta of the whole TI*k-double tile (12.8 KB at k = 50), and restores the column
 //               after the bulk read has drained; the A tile and the B tile alternate (N_j[j] is B with column j from A,
 //               N_nj[j] is A with column j from B), so one bulk store is always in flight while the other tile is patched.
+//               With two store warps (copies = 2) each owns its own copy of the tile pair and every second column.
 // No thread touches the 171 GB going out: per flat block the SM issues ~70 instructions instead of ~40 per 8 bytes.
 // Two addressings of the output: a window [row_begin,row_end) of Sample.flat() (mode 0: export batches), or the BASE-ROW
 // shard [i_lo,i_hi) of every block (mode 1: out[(t*rows + i - i_lo)*k + c]; multi-GPU export: a rank generates only its rows).
+// Measured (C4, k = 50, n = 2^22; tools/export_trace.py, profiles/r02_export_windows.txt): the serial part of a block in the
+// store warp (wait for the buffer, patch, proxy fence, issue) takes 600-900 cycles, a 12.8 KB block at the HBM rate 590.
+//   every block wanted (shard mode, windows longer than k blocks): ONE store warp with A/B alternation writes 7.0 TB/s; two
+//     warps (four stores in flight per SM) only 6.2 TB/s -> copies = 1;
+//   windows of at most k blocks (one family at a time, no alternation): one warp 4.0 TB/s, two warps 5.7 TB/s -> copies = 2.
 // ---------------------------------------------------------------------------------------------
 int launch_sample_flat(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, uint64_t row_begin, uint64_t row_end, double *out);
 
 struct ExportGeom {
     int k, TI, mode;
+    int fast;                        // multiply-only digit loop + computed terms for the large bases (device.cuh: halton_pair)
+    int copies;                      // copies of each tile (A, B): patched blocks of one family in flight at the same time
     uint64_t i_lo, i_hi;             // base rows covered by the launch
     uint64_t row_begin, row_end;     // mode 0: flat-row window
+    int qb, qe;                      // ... its first and last flat row as (block, row in block): row_begin = qb n + rb,
+    uint64_t rb, re;                 //     row_end - 1 = qe n + re
     uint32_t table_len;              // doubles of the term table copied to shared memory (0: read it from global memory)
     uint64_t ntiles;
+    unsigned long long *trace;       // VS_TRACE: clock stamps of CTA 0's first EX_TRACE_TILES tiles ([tile][8]), else nullptr
 };
+constexpr int EX_TRACE_TILES = 48;
+__device__ __forceinline__ void ex_stamp(const ExportGeom &g, uint64_t it, int slot, int lane) {
+    if (g.trace && blockIdx.x == 0 && it < EX_TRACE_TILES && lane == 0) g.trace[it * 16 + slot] = clock64();
+}
 
 #ifndef EX_WAIT_HINT_NS
 #define EX_WAIT_HINT_NS 500u
@@ -194,31 +213,46 @@ __device__ __forceinline__ void ex_commit() { asm volatile("cp.async.bulk.commit
 template <int N> __device__ __forceinline__ void ex_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void ex_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int EX_THREADS = 512, EX_GEN = EX_THREADS - 32;
+constexpr int EX_THREADS = 512, EX_STORE_WARPS = 2, EX_GEN = EX_THREADS - 32 * EX_STORE_WARPS;
+constexpr int EX_AR_D0 = 11, EX_AR_J = 7;    // dimensions >= EX_AR_D0 (bases >= 37): computed terms, no table rows
+
+// doubles of the fixed part of the shared-memory layout (everything before the term table)
+static size_t ex_fixed_doubles(int k) { return 4 + (2 * (size_t)k + 1) / 2 + 3 * (size_t)k + 2 * (size_t)k + 2 * (size_t)k * EX_AR_J; }
 
 __global__ void __launch_bounds__(EX_THREADS, 1)
 sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restrict__ out) {
     extern __shared__ __align__(16) double smem[];
-    const int k = g.k, TI = g.TI;
-    // layout: bars[4] | base[k] off[k] (u32) | magic[k] (u64) | lb[k] wr[k] | table[table_len] | A0 B0 A1 B1 (TI*k each)
+    const int k = g.k, TI = g.TI, NC = g.copies;
+    // layout: bars[4] | base[k] off[k] (u32) | magic[k] (u64) | lb[k] wr[k] | dl[k] | arh arl [k][7] | table[table_len] |
+    //         tiles: per buffer pair (2): per copy (NC): A, B (TI*k each)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                 // full[2], empty[2]
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem + 4);
     uint32_t *soff = sbase + k;
     uint64_t *smagic = reinterpret_cast<uint64_t *>(smem + 4 + ((2 * k + 1) / 2));
     double *slb = reinterpret_cast<double *>(smagic + k);
     double *swr = slb + k;
-    double *table = swr + k;
+    DimLoop *sdl = reinterpret_cast<DimLoop *>(swr + k);
+    double *sarh = reinterpret_cast<double *>(sdl + k), *sarl = sarh + (size_t)k * EX_AR_J;
+    double *table = sarl + (size_t)k * EX_AR_J;
     double *tiles = table + ((g.table_len + 1) & ~1u);
+    const uint32_t table_saddr = ex_smem(table);
     const size_t tile = (size_t)TI * k;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         ex_bar_init(bars + 0, EX_GEN / 32);
         ex_bar_init(bars + 1, EX_GEN / 32);
-        ex_bar_init(bars + 2, 1);
-        ex_bar_init(bars + 3, 1);
+        ex_bar_init(bars + 2, (uint32_t)NC);                   // every store warp releases the buffer pair
+        ex_bar_init(bars + 3, (uint32_t)NC);
     }
     if (!src.raw) {
-        for (int d = tid; d < k; d += EX_THREADS) { sbase[d] = src.h.base[d]; soff[d] = src.h.off[d]; smagic[d] = src.h.magic[d]; }
+        for (int d = tid; d < k; d += EX_THREADS) {
+            sbase[d] = src.h.base[d];
+            soff[d] = src.h.off[d];
+            smagic[d] = src.h.magic[d];
+            if (g.fast) sdl[d] = dim_loop(src.h.base[d], src.start + 2 * src.n - 1);      // the largest index of the design
+        }
+        if (g.fast)
+            for (int e = tid; e < k * EX_AR_J; e += EX_THREADS) { sarh[e] = src.h.arh[e]; sarl[e] = src.h.arl[e]; }
         for (uint32_t e = tid; e < g.table_len; e += EX_THREADS) table[e] = src.h.terms[e];
     }
     for (int d = tid; d < k; d += EX_THREADS) {
@@ -230,21 +264,24 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
     const uint64_t n = src.n;
     const uint64_t my_tiles = blockIdx.x < g.ntiles ? (g.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp != 0) {
+    if (warp >= EX_STORE_WARPS) {
         // ------------------------------------------ generators ------------------------------------------
         // lane = tile row, warp = a set of dimensions: all lanes of a warp walk the SAME base, so the digit loop has one trip
         // count per warp (no divergence), the base / magic / table row are warp-uniform, and the A chain (consecutive indices:
         // conflict-free table reads) and the B chain (permuted indices) of a row advance together as two independent chains.
-        const int gw = warp - 1;
+        const int gw = warp - EX_STORE_WARPS;
         for (uint64_t it = 0; it < my_tiles; ++it) {
             const int pb = (int)(it & 1);
             const uint64_t i0 = g.i_lo + (blockIdx.x + it * gridDim.x) * (uint64_t)TI;
             const int rows = (int)((i0 + TI <= g.i_hi) ? TI : (g.i_hi - i0));
-            double *A = tiles + (size_t)(2 * pb) * tile, *B = A + tile;
+            double *A = tiles + (size_t)(2 * NC * pb) * tile, *B = A + tile;
             const bool live = lane < rows;
             const uint64_t i = i0 + (live ? lane : 0);
+            if (gw == 1) ex_stamp(g, it, 0, lane);
             const uint64_t pi = src.perm[i];
+            if (gw == 1 && pi != ~0ull) ex_stamp(g, it, 1, lane);                        // (the compare makes the stamp wait for the load)
             ex_bar_wait(bars + 2 + pb, (uint32_t)(((it >> 1) & 1) ^ 1));                 // the store warp is done with this buffer pair
+            if (gw == 1) ex_stamp(g, it, 2, lane);
             for (int d = gw; d < k; d += EX_GEN / 32) {
                 double pa, pbv;
                 if (src.raw) {
@@ -260,6 +297,9 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
                     } else if (b == 2u) {
                         pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
                         pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
+                    } else if (g.fast) {
+                        if (d < EX_AR_D0) halton_pair<true>(ma, mb, b, magic, sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pbv);
+                        else halton_pair<false>(ma, mb, b, magic, sdl[d], 0u, sarh + (size_t)d * EX_AR_J, sarl + (size_t)d * EX_AR_J, pa, pbv);
                     } else {
                         const double *row = T + soff[d];
                         pa = 0.0;
@@ -279,22 +319,37 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
                 if (live) {
                     A[(size_t)lane * k + d] = pa;
                     B[(size_t)lane * k + d] = pbv;
+                    if (NC == 2) {
+                        A[2 * tile + (size_t)lane * k + d] = pa;
+                        B[2 * tile + (size_t)lane * k + d] = pbv;
+                    }
                 }
+                if (gw == 1 && pa >= 0.0) ex_stamp(g, it, 8 + min(d / (EX_GEN / 32), 7), lane);
             }
+            if (gw == 1) ex_stamp(g, it, 3, lane);
             ex_fence_async();                                   // my tile entries must be visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0) ex_bar_arrive(bars + pb);
+            if (gw == 1) ex_stamp(g, it, 4, lane);
         }
         return;
     }
-    // ---------------------------------------------- store warp ----------------------------------------------
+    // ---------------------------------------------- store warps ---------------------------------------------
+    // Store warp c owns copy c of the tile pair (A_c, B_c) and the columns j = c mod NC: the serial part of a block -- wait for
+    // the buffer's previous bulk read, restore + patch a column (32 shared stores), proxy fence, issue -- costs 600-900 cycles
+    // of ONE warp (phase stamps, VS_TRACE), more than the 590 cycles a 12.8 KB block may take at the HBM rate; two warps
+    // halve it.  Within a warp the A block and the B block of a column alternate, so one bulk store streams while the other
+    // buffer is patched; a window that covers one family only still has one store in flight per warp.
+    const int sw = warp;
+    if (sw >= NC) return;
     const uint64_t shard = g.i_hi - g.i_lo;
     for (uint64_t it = 0; it < my_tiles; ++it) {
         const int pb = (int)(it & 1);
         const uint64_t i0 = g.i_lo + (blockIdx.x + it * gridDim.x) * (uint64_t)TI;
         const int rows = (int)((i0 + TI <= g.i_hi) ? TI : (g.i_hi - i0));
-        double *A = tiles + (size_t)(2 * pb) * tile, *B = A + tile;
+        double *A = tiles + (size_t)(2 * NC * pb + 2 * sw) * tile, *B = A + tile;        // this warp's copy
         ex_bar_wait(bars + pb, (uint32_t)((it >> 1) & 1));
+        if (sw == 0) ex_stamp(g, it, 5, lane);
         // one block of the flat layout: tile rows [r0, r1) that fall into the window, contiguous in HBM
         auto put = [&](int t, const double *buf) {
             int r0 = 0, r1 = rows;
@@ -310,71 +365,65 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             }
             if (lane == 0) ex_bulk_store(out + orow * (uint64_t)k, buf + (size_t)r0 * k, (uint32_t)((r1 - r0) * k * 8));
         };
-        // blocks [t_min, t_max] of this tile intersect the window (R0(t) = t n + i0 is monotonic in t): two divisions per tile,
-        // then blocks outside cost one integer compare -- no patch, no fence, no wait
+        // blocks [t_min, t_max] of this tile intersect the window (R0(t) = t n + i0 is monotonic in t).  With the window ends
+        // split on the host into (block, row) = (qb, rb) and (qe, re) no division is needed: block t covers the tile's rows
+        // [i0, last] of that block, so t_min = qb if rb <= last else qb + 1, and t_max = qe if i0 <= re else qe - 1.  (The first
+        // form divided two 64-bit numbers per tile: ~2k cycles of the store warp's 6k-cycle fixed cost per tile.)
         int t_min = 0, t_max = 2 * k + 1;
         if (g.mode == 0) {
-            const uint64_t lo_num = g.row_begin > i0 + (uint64_t)rows - 1 ? g.row_begin - i0 - (uint64_t)rows + 1 : 0;   // t n > row_begin - i0 - rows
-            const uint64_t tm = (lo_num + n - 1) / n;
-            t_min = tm > (uint64_t)(2 * k + 2) ? 2 * k + 2 : (int)tm;
-            if (g.row_end <= i0) t_max = -1;
-            else {
-                const uint64_t tx = (g.row_end - 1 - i0) / n;
-                t_max = tx > (uint64_t)(2 * k + 1) ? 2 * k + 1 : (int)tx;
-            }
+            const uint64_t last = i0 + (uint64_t)rows - 1;
+            t_min = g.rb <= last ? g.qb : g.qb + 1;
+            t_max = i0 <= g.re ? g.qe : g.qe - 1;
         }
         auto wanted = [&](int t) { return t >= t_min && t <= t_max; };
-        int last = -1;                                          // tile of the most recent bulk group: 0 = A, 1 = B
-        int pa_col = -1, pb_col = -1;                           // column currently patched in A / B
-        double pa_val = 0.0, pb_val = 0.0;                      // ... and its original value (this lane's row)
-        // Before a tile changes, its own last bulk read must have drained: if the newest group belongs to the OTHER tile,
-        // "all but one group done" is enough (that one keeps streaming while we patch), else everything has to be done.
-        auto quiesce = [&](int tilesel) {
+        // Every bulk store is its own group; groups drain in order.  A buffer may be patched again once ITS last group has
+        // been read out of shared memory: if the newest group belongs to the other buffer, "all but one group done" is enough
+        // (that one keeps streaming while this buffer is patched), else everything has to be done.
+        int lastbuf = -1;                                       // buffer of the newest group: 0 = A, 1 = B
+        int cA = -1, cB = -1;                                   // column currently patched in A / B
+        double vA = 0.0, vB = 0.0;                              // ... and its original value (this lane's row)
+        auto issue = [&](int t, double *buf, int which, int &pcol, double &pval, int col, double orig, double repl) {
             if (lane == 0) {
-                if (last == tilesel) ex_wait_read<0>();
+                if (lastbuf == which) ex_wait_read<0>();
                 else ex_wait_read<1>();
             }
             __syncwarp();
+            if (col >= 0) {
+                if (lane < rows) {
+                    if (pcol >= 0) buf[(size_t)lane * k + pcol] = pval;
+                    buf[(size_t)lane * k + col] = repl;
+                }
+                pcol = col;
+                pval = orig;
+                ex_fence_async();
+                __syncwarp();
+            }
+            put(t, buf);
+            if (lane == 0) ex_commit();
+            lastbuf = which;
         };
-        if (wanted(1)) { put(1, B); if (lane == 0) ex_commit(); last = 1; }          // M_2
-        if (wanted(0)) { put(0, A); if (lane == 0) ex_commit(); last = 0; }          // M_1
-        for (int j = 0; j < k; ++j) {
-            const bool nb = wanted(2 + j), na = wanted(2 + k + j);
+        if (sw == 0 && wanted(1)) issue(1, B, 1, cB, vB, -1, 0.0, 0.0);             // M_2
+        if (sw == NC - 1 && wanted(0)) issue(0, A, 0, cA, vA, -1, 0.0, 0.0);        // M_1
+        // columns j with a wanted block: N_j[j] is block 2 + j, N_nj[j] is block 2 + k + j
+        const int jb_lo = max(t_min - 2, 0), jb_hi = min(t_max - 2, k - 1);                 // N_j
+        const int ja_lo = max(t_min - 2 - k, 0), ja_hi = min(t_max - 2 - k, k - 1);         // N_nj
+        int j_lo = jb_lo <= jb_hi ? (ja_lo <= ja_hi ? min(jb_lo, ja_lo) : jb_lo) : ja_lo;
+        const int j_hi = jb_lo <= jb_hi ? (ja_lo <= ja_hi ? max(jb_hi, ja_hi) : jb_hi) : ja_hi;
+        j_lo += (sw - j_lo % NC + NC) % NC;                     // first column >= j_lo with j = sw mod NC
+        for (int j = j_lo; j <= j_hi; j += NC) {
+            const bool nb = j >= jb_lo && j <= jb_hi, na = j >= ja_lo && j <= ja_hi;
             if (!nb && !na) continue;
-            const double a_j = lane < rows ? A[(size_t)lane * k + j] : 0.0;     // column j is never the patched one (pa_col, pb_col < j)
+            // column j is unpatched in this copy (its patched columns are < j)
+            const double a_j = lane < rows ? A[(size_t)lane * k + j] : 0.0;
             const double b_j = lane < rows ? B[(size_t)lane * k + j] : 0.0;
-            if (nb) {                                           // N_j[j] = B with column j from A
-                quiesce(1);
-                if (lane < rows) {
-                    if (pb_col >= 0) B[(size_t)lane * k + pb_col] = pb_val;
-                    B[(size_t)lane * k + j] = a_j;
-                }
-                pb_col = j;
-                pb_val = b_j;
-                ex_fence_async();
-                __syncwarp();
-                put(2 + j, B);
-                if (lane == 0) ex_commit();
-                last = 1;
-            }
-            if (na) {                                           // N_nj[j] = A with column j from B
-                quiesce(0);
-                if (lane < rows) {
-                    if (pa_col >= 0) A[(size_t)lane * k + pa_col] = pa_val;
-                    A[(size_t)lane * k + j] = b_j;
-                }
-                pa_col = j;
-                pa_val = a_j;
-                ex_fence_async();
-                __syncwarp();
-                put(2 + k + j, A);
-                if (lane == 0) ex_commit();
-                last = 0;
-            }
+            if (nb) issue(2 + j, B, 1, cB, vB, j, b_j, a_j);                        // N_j[j] = B with column j from A
+            if (na) issue(2 + k + j, A, 0, cA, vA, j, a_j, b_j);                    // N_nj[j] = A with column j from B
         }
-        if (lane == 0) ex_wait_read<0>();                       // both tiles may be overwritten by the generators now
+        if (sw == 0) ex_stamp(g, it, 6, lane);
+        if (lane == 0) ex_wait_read<0>();                       // this warp's tile buffers may be overwritten by the generators now
         __syncwarp();
         if (lane == 0) ex_bar_arrive(bars + 2 + pb);
+        if (sw == 0) ex_stamp(g, it, 7, lane);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores complete before the CTA exits
 }
@@ -404,31 +453,75 @@ static int launch_sample_flat_bulk(vs_ctx *c, int k, const SourceDev &src, const
     g.i_hi = i_hi;
     g.row_begin = row_begin;
     g.row_end = row_end;
+    if (mode == 0) {
+        g.qb = (int)(row_begin / src.n);
+        g.rb = row_begin % src.n;
+        g.qe = (int)((row_end - 1) / src.n);
+        g.re = (row_end - 1) % src.n;
+    }
     const size_t avail = c->smem_optin;
-    const size_t fixed = (4 + (2 * (size_t)k + 1) / 2 + 3 * (size_t)k + 2) * sizeof(double);
-    const size_t tab = src.raw ? 0 : (((size_t)src.h.total_terms + 1) & ~(size_t)1) * sizeof(double);
-    // tile height: 32 rows (one lane per row in the store warp) if four tiles fit beside the term table; else without the table
-    int TI = 32;
+    const size_t fixed = (ex_fixed_doubles(k) + 2) * sizeof(double);
+    // fast generator: table rows only for the small bases (dimensions < EX_AR_D0), computed terms for the rest
+    g.fast = (!src.raw && src.h.mode != VS_HALTON_HORNER && src.h.arith_ok && !c->opt.export_slow_gen) ? 1 : 0;
+    size_t tab_terms = src.raw ? 0 : src.h.total_terms;
+    if (g.fast && k > EX_AR_D0) {
+        static const uint32_t small_primes[EX_AR_D0] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
+        tab_terms = 0;
+        for (int d = 0; d < EX_AR_D0; ++d) tab_terms += small_primes[d] * c->halton.ndigits[d];   // terms are laid out dimension by dimension
+    }
+    const size_t tab = ((tab_terms + 1) & ~(size_t)1) * sizeof(double);
+    // tile height: 32 rows (one lane per row in the store warp); two copies of every tile if they fit beside the term table
+    // store warps / tile copies: one when A and B blocks of the same column alternate (every block wanted), else two (see above)
+    int TI = 32, copies = (mode == 1 || g.qe - g.qb >= k) ? 1 : 2;
+    if (c->opt.export_copies == 1 || c->opt.export_copies == 2) copies = c->opt.export_copies;   // VS_EXPORT_COPIES
     bool with_table = !src.raw && src.h.mode != VS_HALTON_HORNER && fixed + tab + 4 * (size_t)TI * k * 8 <= avail;
+    if (g.fast && !with_table) g.fast = 0;                      // (k beyond ~440: generic loop, table in global memory)
     if (!with_table)
         while (TI > 1 && fixed + 4 * (size_t)TI * k * 8 > avail) TI >>= 1;
-    if (fixed + (with_table ? tab : 0) + 4 * (size_t)TI * k * 8 > avail) return VS_OK;
+    if (fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8 > avail) copies = 1;
+    if (fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8 > avail) return VS_OK;
     if (((size_t)TI * k * 8) >= (1u << 20)) return VS_OK;                       // bulk copy size field
     g.TI = TI;
-    g.table_len = with_table ? src.h.total_terms : 0;
+    g.copies = copies;
+    g.table_len = with_table ? (uint32_t)tab_terms : 0;
     g.ntiles = (i_hi - i_lo + TI - 1) / TI;
-    const size_t smem = fixed + (with_table ? tab : 0) + 4 * (size_t)TI * k * 8;
+    const size_t smem = fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8;
     static size_t smem_set[64] = {};
     if (c->device >= 64 || smem_set[c->device] < smem) {
         VS_CUDA(cudaFuncSetAttribute(sample_flat_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (c->device < 64) smem_set[c->device] = smem;
     }
     const unsigned grid = (unsigned)(g.ntiles < (uint64_t)c->sm_count ? g.ntiles : (uint64_t)c->sm_count);
+    g.trace = nullptr;
+    if (!c->opt.trace.empty()) {
+        VS_CUDA(cudaMalloc(&g.trace, EX_TRACE_TILES * 16 * sizeof(unsigned long long)));
+        VS_CUDA(cudaMemsetAsync(g.trace, 0, EX_TRACE_TILES * 16 * sizeof(unsigned long long), c->stream));
+    }
     time_begin(c);
     sample_flat_bulk_kernel<<<grid, EX_THREADS, smem, c->stream>>>(g, src, s, out);
     time_end(c);
     c->launches++;
     VS_CUDA(cudaGetLastError());
+    if (g.trace) {
+        // CTA 0, per tile: generator warp 1: loop top, perm loaded, buffer free, tile generated, arrived | store warp: tile
+        // full, stores issued, buffer released -- cycles relative to the first stamp
+        std::vector<unsigned long long> h(EX_TRACE_TILES * 16);
+        VS_CUDA(cudaStreamSynchronize(c->stream));
+        VS_CUDA(cudaMemcpy(h.data(), g.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        VS_CUDA(cudaFree(g.trace));
+        if (FILE *f = fopen(c->opt.trace.c_str(), "a")) {
+            fprintf(f, "# sample_flat_bulk_kernel k=%d TI=%d copies=%d fast=%d mode=%d tiles/CTA=%llu: tile | gen: top perm free done arrived | store: full issued released\n",
+                    k, g.TI, g.copies, g.fast, mode, (unsigned long long)((g.ntiles + grid - 1) / grid));
+            for (int t = 0; t < EX_TRACE_TILES && h[t * 16]; ++t) {
+                fprintf(f, "%3d |", t);
+                for (int q = 0; q < 8; ++q) fprintf(f, " %8lld%s", (long long)(h[t * 16 + q] - h[0]), q == 4 ? " |" : "");
+                fprintf(f, " | dims of generator warp 1 done at:");
+                for (int q = 8; q < 16 && h[t * 16 + q]; ++q) fprintf(f, " %8lld", (long long)(h[t * 16 + q] - h[0]));
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     *done = true;
     return VS_OK;
 }

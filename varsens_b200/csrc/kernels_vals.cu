@@ -105,19 +105,26 @@ template <class F>
 __global__ void __launch_bounds__(PF_WARPS * 32, 2)
 eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end, uint32_t table_len, double *__restrict__ fvals) {
     extern __shared__ __align__(16) double smem[];
-    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
+    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | dl[k] | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem);
     uint32_t *soff = sbase + k;
     uint64_t *smagic = reinterpret_cast<uint64_t *>(smem + ((2 * k + 1) / 2));
     double *slb = reinterpret_cast<double *>(smagic + k);
     double *swr = slb + k;
     double *sarh = swr + k, *sarl = sarh + (size_t)k * PF_AR_J;
-    double *table = sarl + (size_t)k * PF_AR_J;
+    DimLoop *sdl = reinterpret_cast<DimLoop *>(sarl + (size_t)k * PF_AR_J);       // 16 bytes per dimension
+    double *table = reinterpret_cast<double *>(sdl + k);
+    const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(table);
     double *TA = table + table_len, *TB = TA + (size_t)k * 32;
     double *PA = TB + (size_t)k * 32, *PB = PA + (size_t)(k + 1) * 32, *SA = PB + (size_t)(k + 1) * 32, *SB = SA + (size_t)(k + 1) * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (!src.raw) {
-        for (int d = tid; d < k; d += blockDim.x) { sbase[d] = src.h.base[d]; soff[d] = src.h.off[d]; smagic[d] = src.h.magic[d]; }
+        for (int d = tid; d < k; d += blockDim.x) {
+            sbase[d] = src.h.base[d];
+            soff[d] = src.h.off[d];
+            smagic[d] = src.h.magic[d];
+            sdl[d] = dim_loop(src.h.base[d], src.start + 2 * src.n - 1);          // the largest index of the design
+        }
         for (int e = tid; e < k * PF_AR_J; e += blockDim.x) { sarh[e] = src.h.arh[e]; sarl[e] = src.h.arl[e]; }
         for (uint32_t e = tid; e < table_len; e += blockDim.x) table[e] = src.h.terms[e];
     }
@@ -141,36 +148,16 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
                 pb = src.raw[(n + pi) * (uint64_t)k + d];
             } else {
                 const uint32_t b = sbase[d];
-                const uint64_t magic = smagic[d];
-                uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
+                const uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
                 if (b == 2u) {
                     pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
                     pb = (double)__brev(mb) * 2.3283064365386962890625e-10;
                 } else if (d < PF_AR_D0) {
-                    const double *row = table + soff[d];
-                    pa = 0.0;
-                    pb = 0.0;
-                    while ((ma | mb) != 0u) {                           // an exhausted index keeps adding row[0] == 0.0: exact
-                        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
-                        pa = __dadd_rn(pa, row[ma - qa * b]);
-                        pb = __dadd_rn(pb, row[mb - qb * b]);
-                        row += b;
-                        ma = qa;
-                        mb = qb;
-                    }
+                    // table terms for the small bases (rows of <= 31 doubles: conflict-free or nearly so), multiply-only digit loop
+                    halton_pair<true>(ma, mb, b, smagic[d], sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pb);
                 } else {
                     // computed terms: digit / b^(j+1) = fma(dd, rh, dd * rl), dd = 8 * digit (fused_impl.cuh: digit_step_arith)
-                    const double *rh = sarh + (size_t)d * PF_AR_J, *rl = sarl + (size_t)d * PF_AR_J;
-                    pa = 0.0;
-                    pb = 0.0;
-                    for (int j = 0; (ma | mb) != 0u; ++j) {
-                        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
-                        const double da = (double)(8u * (ma - qa * b)), db = (double)(8u * (mb - qb * b));
-                        pa = __dadd_rn(pa, __fma_rn(da, rh[j], __dmul_rn(da, rl[j])));
-                        pb = __dadd_rn(pb, __fma_rn(db, rh[j], __dmul_rn(db, rl[j])));
-                        ma = qa;
-                        mb = qb;
-                    }
+                    halton_pair<false>(ma, mb, b, smagic[d], sdl[d], 0u, sarh + (size_t)d * PF_AR_J, sarl + (size_t)d * PF_AR_J, pa, pb);
                 }
             }
             if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pb = __dadd_rn(__dmul_rn(pb, swr[d]), slb[d]); }
@@ -225,7 +212,7 @@ static int launch_eval_pf(vs_ctx *c, int k, const SourceDev &src, const ScaleDev
         for (int d = 0; d < k && d < PF_AR_D0; ++d) table_len += small_primes[d] * c->halton.ndigits[d];
         if (k <= PF_AR_D0) table_len = src.h.total_terms;
     }
-    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + table_len + 2 * (size_t)k * 32 +
+    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + 2 * (size_t)k + table_len + 2 * (size_t)k * 32 +
                            4 * (size_t)(k + 1) * 32 + 2;
     const size_t smem = doubles * sizeof(double);
     if (smem > c->smem_optin) return VS_OK;

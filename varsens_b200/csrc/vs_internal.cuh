@@ -120,6 +120,8 @@ struct Options {
     int debug_skip = 0;         // VS_DEBUG_SKIP
     std::string trace;          // VS_TRACE          file for CTA 0's clock stamps
     int gram_mma = -1;          // VS_GRAM_MMA       (-1 = default)
+    int export_slow_gen = 0;    // VS_EXPORT_SLOW_GEN=1: generic digit loop in the bulk export kernel (comparison runs)
+    int export_copies = 0;      // VS_EXPORT_COPIES=1|2: store warps / tile copies of the bulk export kernel (0: by window shape)
     int gram_mma_gen = -1;      // VS_GRAM_GEN       0: register-tile kernel for l > 1 outputs / odd row counts
     int gram_st = 0, gram_rc = 0, gram_stages = 0, gram_hint = 0x989680, gram_debug = 0;
     int p2p_timeout_ms = 10000; // VS_P2P_TIMEOUT_MS bounded wait for the peers' flags in the exchange
