@@ -11,6 +11,8 @@ tag = "copies=%s slowgen=%s" % (os.environ.get("VS_EXPORT_COPIES", "2"), os.envi
 for what in sys.argv[1:] or ["gen", "w16"]:
     if what == "gen":
         out = torch.empty((2, k), dtype=torch.float64, device="cuda"); r0, r1 = n - 1, n + 1
+    elif what == "full":
+        rows = 2 * n * (1 + k); out = torch.empty((rows, k), dtype=torch.float64, device="cuda"); r0, r1 = 0, rows
     elif what in ("w16", "w64", "w1"):
         rows = int({"w16": 16e9, "w64": 64e9, "w1": 1e9}[what] / (k * 8)); out = torch.empty((rows, k), dtype=torch.float64, device="cuda"); r0, r1 = n + 12345, n + 12345 + rows
     ts = []

@@ -112,6 +112,141 @@ __device__ __forceinline__ void halton_pair(uint32_t ma, uint32_t mb, uint32_t b
     }
 }
 
+// Two dimensions with computed terms at once: four chains (A and B index of the row in dimensions d1 and d2) share one
+// loop -- half the loop and branch overhead per dimension and twice the independent work per warp.  The trip counts are
+// the larger ones of the two dimensions: a general division step is exact for any index, and a position beyond a
+// dimension's last digit adds fma(0, rh, 0 * rl) = +0.0.
+__device__ __forceinline__ void halton_quad_arith(uint32_t ia, uint32_t ib, uint32_t b1, uint64_t magic1, const DimLoop dl1,
+                                                  const double *__restrict__ rh1, const double *__restrict__ rl1, uint32_t b2,
+                                                  uint64_t magic2, const DimLoop dl2, const double *__restrict__ rh2,
+                                                  const double *__restrict__ rl2, double &pa1, double &pb1, double &pa2, double &pb2) {
+    auto term = [](uint32_t off8, double rh, double rl) -> double {
+        const double dd = __dadd_rn(__hiloint2double(0x43300000, (int)off8), -4503599627370496.0);       // 2^52 + off8, exact
+        return __fma_rn(dd, rh, __dmul_rn(dd, rl));
+    };
+    uint32_t ma1 = ia, mb1 = ib, ma2 = ia, mb2 = ib;
+    pa1 = 0.0; pb1 = 0.0; pa2 = 0.0; pb2 = 0.0;
+    const int jg = max(dl1.jg, dl2.jg), nd = max(dl1.nd, dl2.nd);
+    int j = 0;
+#pragma unroll 1
+    for (; j < jg; ++j) {                                     // usually 0 or 1 trips
+        const uint32_t qa1 = (uint32_t)__umul64hi((uint64_t)ma1, magic1), qb1 = (uint32_t)__umul64hi((uint64_t)mb1, magic1);
+        const uint32_t qa2 = (uint32_t)__umul64hi((uint64_t)ma2, magic2), qb2 = (uint32_t)__umul64hi((uint64_t)mb2, magic2);
+        const double h1 = rh1[j], l1 = rl1[j], h2 = rh2[j], l2 = rl2[j];
+        pa1 = __dadd_rn(pa1, term(8u * (ma1 - qa1 * b1), h1, l1));
+        pb1 = __dadd_rn(pb1, term(8u * (mb1 - qb1 * b1), h1, l1));
+        pa2 = __dadd_rn(pa2, term(8u * (ma2 - qa2 * b2), h2, l2));
+        pb2 = __dadd_rn(pb2, term(8u * (mb2 - qb2 * b2), h2, l2));
+        ma1 = qa1; mb1 = qb1; ma2 = qa2; mb2 = qb2;
+    }
+#pragma unroll 1
+    for (; j < nd; ++j) {
+        const uint64_t wa1 = (uint64_t)ma1 * dl1.c32, wb1 = (uint64_t)mb1 * dl1.c32;
+        const uint64_t wa2 = (uint64_t)ma2 * dl2.c32, wb2 = (uint64_t)mb2 * dl2.c32;
+        const double h1 = rh1[j], l1 = rl1[j], h2 = rh2[j], l2 = rl2[j];
+        ma1 = (uint32_t)(wa1 >> 32); mb1 = (uint32_t)(wb1 >> 32);
+        ma2 = (uint32_t)(wa2 >> 32); mb2 = (uint32_t)(wb2 >> 32);
+        pa1 = __dadd_rn(pa1, term(__umulhi((uint32_t)wa1, dl1.b8), h1, l1));
+        pb1 = __dadd_rn(pb1, term(__umulhi((uint32_t)wb1, dl1.b8), h1, l1));
+        pa2 = __dadd_rn(pa2, term(__umulhi((uint32_t)wa2, dl2.b8), h2, l2));
+        pb2 = __dadd_rn(pb2, term(__umulhi((uint32_t)wb2, dl2.b8), h2, l2));
+    }
+}
+
+// Shared-memory constants of the run-time-base generators (export mode, product-form evaluation), filled once per CTA.
+constexpr int HL_D0 = 11;      // dimensions >= HL_D0 (bases >= 37): computed terms; below: table rows in shared memory
+constexpr int HL_J = 7;        // digit positions of a 32-bit index in base >= 37 (layout of HaltonDev::arh / arl)
+struct HaltonShared {
+    const uint32_t *base, *off;
+    const uint64_t *magic;
+    const DimLoop *dl;
+    const double *arh, *arl;
+    uint32_t table_saddr;      // shared-window byte address of the table prefix (dimensions < HL_D0)
+};
+
+// The unscaled coordinates of one row pair (A index ia, B index ib), lane = row, distributed over the warps of a team by
+// UNITS: unit u < min(k, HL_D0) is the single dimension u (base 2: a bit reversal; bases 3..31: table terms), the units after
+// those are PAIRS of computed-term dimensions (HL_D0 + 2p, HL_D0 + 2p + 1).  ulist[w * HL_MAXQ + q] is the q-th unit of warp w,
+// 255 ends the list (halton_schedule); emit(d, pa, pb) receives every coordinate once.  All branches are warp-uniform.
+constexpr int HL_MAXQ = 32;            // units per warp at most
+constexpr int HL_MAX_UNITS = 160;      // k <= 309: at most 20 units per warp on average with 8 warps
+constexpr int HL_LIST_BYTES = 16 * HL_MAXQ;   // up to 16 warps
+__host__ __device__ inline int halton_unit_count(int k) {
+    const int nsmall = k < HL_D0 ? k : HL_D0;
+    return nsmall + (k - nsmall + 1) / 2;
+}
+
+// Longest-processing-time assignment of the units to `nw` warps (one thread, once per CTA).  A unit's cost is its digit
+// count plus a fixed part (measured with per-dimension clock stamps in the export kernel: ~0.4 k cycles fixed, ~0.11 k per
+// digit step of a two-chain loop, a four-chain pair step ~2.2x that).  Both unit lists are already in descending cost order
+// (digit counts fall with the base), so a merge replaces the sort.  Round-robin assignment left the warps that own the base-3
+// and base-5 dimensions with 5.0 k cycles per tile against an average of 2.9 k.
+__device__ inline void halton_schedule(int k, int nw, const DimLoop *dl, unsigned char *ulist) {
+    const int nsmall = k < HL_D0 ? k : HL_D0, nunits = halton_unit_count(k);
+    float load[16];
+    int cnt[16];
+    for (int w = 0; w < nw; ++w) { load[w] = 0.0f; cnt[w] = 0; }
+    for (int e = 0; e < nw * HL_MAXQ; ++e) ulist[e] = 255;
+    auto cost_pair = [&](int u) {
+        const int d1 = HL_D0 + 2 * (u - nsmall), d2 = d1 + 1;
+        return d2 < k ? 4.0f + 2.2f * (float)max(dl[d1].nd, dl[d2].nd) : 4.0f + 1.2f * (float)dl[d1].nd;
+    };
+    auto place = [&](int u, float c) {
+        int best = -1;
+        for (int w = 0; w < nw; ++w)
+            if (cnt[w] < HL_MAXQ - 1 && (best < 0 || load[w] < load[best])) best = w;
+        load[best] += c;
+        ulist[best * HL_MAXQ + cnt[best]++] = (unsigned char)u;
+    };
+    int is = 1, ip = nsmall;
+    while (is < nsmall || ip < nunits) {
+        const float cs = is < nsmall ? 4.0f + (float)dl[is].nd : -1.0f;
+        const float cp = ip < nunits ? cost_pair(ip) : -1.0f;
+        if (cs >= cp) place(is++, cs);
+        else place(ip++, cp);
+    }
+    if (nunits > 0) place(0, 1.0f);                          // dimension 0: base 2, a bit reversal
+}
+
+template <class Emit>
+__device__ __forceinline__ void halton_units(int w, const unsigned char *__restrict__ ulist, int k, uint32_t ia, uint32_t ib,
+                                             const HaltonShared &hs, Emit &&emit) {
+    const int nsmall = k < HL_D0 ? k : HL_D0;
+    const uint32_t *wl = reinterpret_cast<const uint32_t *>(ulist + w * HL_MAXQ);      // four units per load
+    uint32_t pack = wl[0];
+    for (int q = 0;; ++q) {
+        if (q && (q & 3) == 0) pack = wl[q >> 2];
+        const int u = (int)(pack & 255u);
+        pack >>= 8;
+        if (u == 255) break;
+        if (u < nsmall) {
+            const uint32_t b = hs.base[u];
+            double pa, pb;
+            if (b == 2u) {
+                pa = (double)__brev(ia) * 2.3283064365386962890625e-10;
+                pb = (double)__brev(ib) * 2.3283064365386962890625e-10;
+            } else {
+                halton_pair<true>(ia, ib, b, hs.magic[u], hs.dl[u], hs.table_saddr + 8u * hs.off[u], nullptr, nullptr, pa, pb);
+            }
+            emit(u, pa, pb);
+        } else {
+            const int d1 = HL_D0 + 2 * (u - nsmall), d2 = d1 + 1;
+            if (d2 < k) {
+                double pa1, pb1, pa2, pb2;
+                halton_quad_arith(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J,
+                                  hs.base[d2], hs.magic[d2], hs.dl[d2], hs.arh + (size_t)d2 * HL_J, hs.arl + (size_t)d2 * HL_J, pa1, pb1,
+                                  pa2, pb2);
+                emit(d1, pa1, pb1);
+                emit(d2, pa2, pb2);
+            } else {
+                double pa, pb;
+                halton_pair<false>(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], 0u, hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J, pa, pb);
+                emit(d1, pa, pb);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // scale.py:33 (two roundings: multiply, then add -- never an FMA) and :62.
 // ---------------------------------------------------------------------------------------------

@@ -214,16 +214,16 @@ template <int N> __device__ __forceinline__ void ex_wait_read() { asm volatile("
 __device__ __forceinline__ void ex_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int EX_THREADS = 512, EX_STORE_WARPS = 2, EX_GEN = EX_THREADS - 32 * EX_STORE_WARPS;
-constexpr int EX_AR_D0 = 11, EX_AR_J = 7;    // dimensions >= EX_AR_D0 (bases >= 37): computed terms, no table rows
+constexpr int EX_AR_D0 = HL_D0, EX_AR_J = HL_J;    // dimensions >= EX_AR_D0 (bases >= 37): computed terms, no table rows
 
 // doubles of the fixed part of the shared-memory layout (everything before the term table)
-static size_t ex_fixed_doubles(int k) { return 4 + (2 * (size_t)k + 1) / 2 + 3 * (size_t)k + 2 * (size_t)k + 2 * (size_t)k * EX_AR_J; }
+static size_t ex_fixed_doubles(int k) { return 4 + (2 * (size_t)k + 1) / 2 + 3 * (size_t)k + 2 * (size_t)k + 2 * (size_t)k * EX_AR_J + HL_LIST_BYTES / 8; }
 
 __global__ void __launch_bounds__(EX_THREADS, 1)
 sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restrict__ out) {
     extern __shared__ __align__(16) double smem[];
     const int k = g.k, TI = g.TI, NC = g.copies;
-    // layout: bars[4] | base[k] off[k] (u32) | magic[k] (u64) | lb[k] wr[k] | dl[k] | arh arl [k][7] | table[table_len] |
+    // layout: bars[4] | base[k] off[k] (u32) | magic[k] (u64) | lb[k] wr[k] | dl[k] | arh arl [k][7] | ulist[16][32] (u8) | table[table_len] |
     //         tiles: per buffer pair (2): per copy (NC): A, B (TI*k each)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                 // full[2], empty[2]
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem + 4);
@@ -233,7 +233,8 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
     double *swr = slb + k;
     DimLoop *sdl = reinterpret_cast<DimLoop *>(swr + k);
     double *sarh = reinterpret_cast<double *>(sdl + k), *sarl = sarh + (size_t)k * EX_AR_J;
-    double *table = sarl + (size_t)k * EX_AR_J;
+    unsigned char *uwarp = reinterpret_cast<unsigned char *>(sarl + (size_t)k * EX_AR_J);   // [warp][HL_MAXQ]: the units of every generator warp
+    double *table = sarl + (size_t)k * EX_AR_J + HL_LIST_BYTES / 8;
     double *tiles = table + ((g.table_len + 1) & ~1u);
     const uint32_t table_saddr = ex_smem(table);
     const size_t tile = (size_t)TI * k;
@@ -260,7 +261,10 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
         swr[d] = s.kind != VS_SCALE_IDENTITY ? s.wr[d] : 1.0;
     }
     __syncthreads();
+    if (g.fast == 1 && tid == 0) halton_schedule(k, EX_GEN / 32, sdl, uwarp);
+    __syncthreads();
     const double *T = g.table_len ? table : src.h.terms;
+    const HaltonShared hs{sbase, soff, smagic, sdl, sarh, sarl, table_saddr};
     const uint64_t n = src.n;
     const uint64_t my_tiles = blockIdx.x < g.ntiles ? (g.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -282,38 +286,7 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             if (gw == 1 && pi != ~0ull) ex_stamp(g, it, 1, lane);                        // (the compare makes the stamp wait for the load)
             ex_bar_wait(bars + 2 + pb, (uint32_t)(((it >> 1) & 1) ^ 1));                 // the store warp is done with this buffer pair
             if (gw == 1) ex_stamp(g, it, 2, lane);
-            for (int d = gw; d < k; d += EX_GEN / 32) {
-                double pa, pbv;
-                if (src.raw) {
-                    pa = src.raw[i * (uint64_t)k + d];
-                    pbv = src.raw[(n + pi) * (uint64_t)k + d];
-                } else {
-                    const uint32_t b = sbase[d];
-                    const uint64_t magic = smagic[d];
-                    uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
-                    if (src.h.mode == VS_HALTON_HORNER) {
-                        pa = radical_inverse_horner(b, magic, ma);
-                        pbv = radical_inverse_horner(b, magic, mb);
-                    } else if (b == 2u) {
-                        pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
-                        pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
-                    } else if (g.fast) {
-                        if (d < EX_AR_D0) halton_pair<true>(ma, mb, b, magic, sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pbv);
-                        else halton_pair<false>(ma, mb, b, magic, sdl[d], 0u, sarh + (size_t)d * EX_AR_J, sarl + (size_t)d * EX_AR_J, pa, pbv);
-                    } else {
-                        const double *row = T + soff[d];
-                        pa = 0.0;
-                        pbv = 0.0;
-                        while ((ma | mb) != 0u) {                       // an exhausted index keeps adding row[0] == 0.0: exact
-                            const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
-                            pa = __dadd_rn(pa, row[ma - qa * b]);
-                            pbv = __dadd_rn(pbv, row[mb - qb * b]);
-                            row += b;
-                            ma = qa;
-                            mb = qb;
-                        }
-                    }
-                }
+            auto emit = [&](int d, double pa, double pbv) {
                 if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pbv = __dadd_rn(__dmul_rn(pbv, swr[d]), slb[d]); }
                 else if (s.kind == VS_SCALE_POWER) { pa = __dmul_rn(slb[d], pow(swr[d], pa)); pbv = __dmul_rn(slb[d], pow(swr[d], pbv)); }
                 if (live) {
@@ -324,7 +297,54 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
                         B[2 * tile + (size_t)lane * k + d] = pbv;
                     }
                 }
-                if (gw == 1 && pa >= 0.0) ex_stamp(g, it, 8 + min(d / (EX_GEN / 32), 7), lane);
+            };
+            if (g.fast == 1) {
+                // units of one table dimension or two computed-term dimensions, balanced over the generator warps (halton_schedule)
+                halton_units(gw, uwarp, k, (uint32_t)(src.start + i), (uint32_t)(src.start + n + pi), hs, emit);
+            } else if (g.fast == 2) {
+                // comparison form (VS_EXPORT_SLOW_GEN=2): one dimension at a time, round-robin over the generator warps
+                for (int d = gw; d < k; d += EX_GEN / 32) {
+                    const uint32_t b = sbase[d], ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
+                    double pa, pbv;
+                    if (b == 2u) {
+                        pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
+                        pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
+                    } else if (d < EX_AR_D0) halton_pair<true>(ma, mb, b, smagic[d], sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pbv);
+                    else halton_pair<false>(ma, mb, b, smagic[d], sdl[d], 0u, sarh + (size_t)d * EX_AR_J, sarl + (size_t)d * EX_AR_J, pa, pbv);
+                    emit(d, pa, pbv);
+                }
+            } else {
+                for (int d = gw; d < k; d += EX_GEN / 32) {
+                    double pa, pbv;
+                    if (src.raw) {
+                        pa = src.raw[i * (uint64_t)k + d];
+                        pbv = src.raw[(n + pi) * (uint64_t)k + d];
+                    } else {
+                        const uint32_t b = sbase[d];
+                        const uint64_t magic = smagic[d];
+                        uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
+                        if (src.h.mode == VS_HALTON_HORNER) {
+                            pa = radical_inverse_horner(b, magic, ma);
+                            pbv = radical_inverse_horner(b, magic, mb);
+                        } else if (b == 2u) {
+                            pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
+                            pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
+                        } else {
+                            const double *row = T + soff[d];
+                            pa = 0.0;
+                            pbv = 0.0;
+                            while ((ma | mb) != 0u) {                       // an exhausted index keeps adding row[0] == 0.0: exact
+                                const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
+                                pa = __dadd_rn(pa, row[ma - qa * b]);
+                                pbv = __dadd_rn(pbv, row[mb - qb * b]);
+                                row += b;
+                                ma = qa;
+                                mb = qb;
+                            }
+                        }
+                    }
+                    emit(d, pa, pbv);
+                }
             }
             if (gw == 1) ex_stamp(g, it, 3, lane);
             ex_fence_async();                                   // my tile entries must be visible to the TMA (async proxy)
@@ -350,21 +370,6 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
         double *A = tiles + (size_t)(2 * NC * pb + 2 * sw) * tile, *B = A + tile;        // this warp's copy
         ex_bar_wait(bars + pb, (uint32_t)((it >> 1) & 1));
         if (sw == 0) ex_stamp(g, it, 5, lane);
-        // one block of the flat layout: tile rows [r0, r1) that fall into the window, contiguous in HBM
-        auto put = [&](int t, const double *buf) {
-            int r0 = 0, r1 = rows;
-            uint64_t orow;
-            if (g.mode == 0) {
-                const uint64_t R0 = (uint64_t)t * n + i0;
-                if (R0 + rows <= g.row_begin || R0 >= g.row_end) return;
-                if (R0 < g.row_begin) r0 = (int)(g.row_begin - R0);
-                if (R0 + rows > g.row_end) r1 = (int)(g.row_end - R0);
-                orow = R0 + r0 - g.row_begin;
-            } else {
-                orow = (uint64_t)t * shard + (i0 - g.i_lo);
-            }
-            if (lane == 0) ex_bulk_store(out + orow * (uint64_t)k, buf + (size_t)r0 * k, (uint32_t)((r1 - r0) * k * 8));
-        };
         // blocks [t_min, t_max] of this tile intersect the window (R0(t) = t n + i0 is monotonic in t).  With the window ends
         // split on the host into (block, row) = (qb, rb) and (qe, re) no division is needed: block t covers the tile's rows
         // [i0, last] of that block, so t_min = qb if rb <= last else qb + 1, and t_max = qe if i0 <= re else qe - 1.  (The first
@@ -376,6 +381,24 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             t_max = i0 <= g.re ? g.qe : g.qe - 1;
         }
         auto wanted = [&](int t) { return t >= t_min && t <= t_max; };
+        // one block of the flat layout: tile rows [r0, r1) that fall into the window, contiguous in HBM.  Only the first and
+        // the last wanted block of a tile can be clipped; everything else is tile_dst + t * blk.  The descriptor is computed
+        // BEFORE the wait for the buffer (the asm statements are ordering points for the compiler): the store warp's serial
+        // work per block is what bounds the kernel (~560 cycles per 12.8 KB block, phase stamps), so nothing that can be done
+        // early may sit between the wait and the bulk store.
+        const uint64_t blk = (g.mode == 0 ? n : shard) * (uint64_t)k;                        // doubles per block of the output
+        double *tile_dst = g.mode == 0 ? out + ((int64_t)i0 - (int64_t)g.row_begin) * (int64_t)k : out + (i0 - g.i_lo) * (uint64_t)k;
+        auto describe = [&](int t, double *&dst, uint32_t &src_off, uint32_t &bytes) {
+            int r0 = 0, r1 = rows;
+            if (g.mode == 0 && (t == t_min || t == t_max)) {
+                const uint64_t R0 = (uint64_t)t * n + i0;
+                if (R0 < g.row_begin) r0 = (int)(g.row_begin - R0);
+                if (R0 + rows > g.row_end) r1 = (int)(g.row_end - R0);
+            }
+            dst = tile_dst + (uint64_t)t * blk + (uint64_t)r0 * k;
+            src_off = (uint32_t)r0 * (uint32_t)k;
+            bytes = (uint32_t)((r1 - r0) * k * 8);
+        };
         // Every bulk store is its own group; groups drain in order.  A buffer may be patched again once ITS last group has
         // been read out of shared memory: if the newest group belongs to the other buffer, "all but one group done" is enough
         // (that one keeps streaming while this buffer is patched), else everything has to be done.
@@ -383,6 +406,9 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
         int cA = -1, cB = -1;                                   // column currently patched in A / B
         double vA = 0.0, vB = 0.0;                              // ... and its original value (this lane's row)
         auto issue = [&](int t, double *buf, int which, int &pcol, double &pval, int col, double orig, double repl) {
+            double *dst;
+            uint32_t src_off, bytes;
+            describe(t, dst, src_off, bytes);
             if (lane == 0) {
                 if (lastbuf == which) ex_wait_read<0>();
                 else ex_wait_read<1>();
@@ -398,8 +424,10 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
                 ex_fence_async();
                 __syncwarp();
             }
-            put(t, buf);
-            if (lane == 0) ex_commit();
+            if (lane == 0) {
+                ex_bulk_store(dst, buf + src_off, bytes);
+                ex_commit();
+            }
             lastbuf = which;
         };
         if (sw == 0 && wanted(1)) issue(1, B, 1, cB, vB, -1, 0.0, 0.0);             // M_2
@@ -462,7 +490,7 @@ static int launch_sample_flat_bulk(vs_ctx *c, int k, const SourceDev &src, const
     const size_t avail = c->smem_optin;
     const size_t fixed = (ex_fixed_doubles(k) + 2) * sizeof(double);
     // fast generator: table rows only for the small bases (dimensions < EX_AR_D0), computed terms for the rest
-    g.fast = (!src.raw && src.h.mode != VS_HALTON_HORNER && src.h.arith_ok && !c->opt.export_slow_gen) ? 1 : 0;
+    g.fast = (!src.raw && src.h.mode != VS_HALTON_HORNER && src.h.arith_ok && c->opt.export_slow_gen != 1) ? (c->opt.export_slow_gen == 2 ? 2 : 1) : 0;
     size_t tab_terms = src.raw ? 0 : src.h.total_terms;
     if (g.fast && k > EX_AR_D0) {
         static const uint32_t small_primes[EX_AR_D0] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
@@ -475,7 +503,7 @@ static int launch_sample_flat_bulk(vs_ctx *c, int k, const SourceDev &src, const
     int TI = 32, copies = (mode == 1 || g.qe - g.qb >= k) ? 1 : 2;
     if (c->opt.export_copies == 1 || c->opt.export_copies == 2) copies = c->opt.export_copies;   // VS_EXPORT_COPIES
     bool with_table = !src.raw && src.h.mode != VS_HALTON_HORNER && fixed + tab + 4 * (size_t)TI * k * 8 <= avail;
-    if (g.fast && !with_table) g.fast = 0;                      // (k beyond ~440: generic loop, table in global memory)
+    if (g.fast && (!with_table || halton_unit_count(k) > HL_MAX_UNITS)) g.fast = 0;   // (k beyond ~440: generic loop, table in global memory)
     if (!with_table)
         while (TI > 1 && fixed + 4 * (size_t)TI * k * 8 > avail) TI >>= 1;
     if (fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8 > avail) copies = 1;
@@ -485,7 +513,9 @@ static int launch_sample_flat_bulk(vs_ctx *c, int k, const SourceDev &src, const
     g.copies = copies;
     g.table_len = with_table ? (uint32_t)tab_terms : 0;
     g.ntiles = (i_hi - i_lo + TI - 1) / TI;
-    const size_t smem = fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8;
+    size_t smem = fixed + (with_table ? tab : 0) + 4 * (size_t)copies * TI * k * 8;
+    if (c->opt.export_smem_kb > 0 && smem < (size_t)c->opt.export_smem_kb * 1024) smem = (size_t)c->opt.export_smem_kb * 1024;   // VS_EXPORT_SMEM_KB
+    if (smem > avail) smem = avail;
     static size_t smem_set[64] = {};
     if (c->device >= 64 || smem_set[c->device] < smem) {
         VS_CUDA(cudaFuncSetAttribute(sample_flat_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

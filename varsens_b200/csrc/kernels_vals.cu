@@ -99,13 +99,13 @@ __global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, Scal
 // this phase to ~1.5 (tools/bench_configs.py).  The values are the same products associated differently (prefix * term *
 // suffix instead of left to right): <= 2 ulp from F::operator(), far inside the 1e-10 contract on the indices.
 // ---------------------------------------------------------------------------------------------
-constexpr int PF_AR_D0 = 11, PF_AR_J = 7, PF_WARPS = 8;
+constexpr int PF_AR_D0 = HL_D0, PF_AR_J = HL_J, PF_WARPS = 8;
 
 template <class F>
 __global__ void __launch_bounds__(PF_WARPS * 32, 2)
 eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end, uint32_t table_len, double *__restrict__ fvals) {
     extern __shared__ __align__(16) double smem[];
-    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | dl[k] | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
+    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | dl[k] | ulist[16][32] (u8) | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem);
     uint32_t *soff = sbase + k;
     uint64_t *smagic = reinterpret_cast<uint64_t *>(smem + ((2 * k + 1) / 2));
@@ -113,7 +113,8 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
     double *swr = slb + k;
     double *sarh = swr + k, *sarl = sarh + (size_t)k * PF_AR_J;
     DimLoop *sdl = reinterpret_cast<DimLoop *>(sarl + (size_t)k * PF_AR_J);       // 16 bytes per dimension
-    double *table = reinterpret_cast<double *>(sdl + k);
+    unsigned char *uwarp = reinterpret_cast<unsigned char *>(sdl + k);            // [warp][HL_MAXQ]: the units of every warp
+    double *table = reinterpret_cast<double *>(sdl + k) + HL_LIST_BYTES / 8;
     const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(table);
     double *TA = table + table_len, *TB = TA + (size_t)k * 32;
     double *PA = TB + (size_t)k * 32, *PB = PA + (size_t)(k + 1) * 32, *SA = PB + (size_t)(k + 1) * 32, *SB = SA + (size_t)(k + 1) * 32;
@@ -133,6 +134,9 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
         swr[d] = s.kind != VS_SCALE_IDENTITY ? s.wr[d] : 1.0;
     }
     __syncthreads();
+    if (!src.raw && tid == 0) halton_schedule(k, PF_WARPS, sdl, uwarp);
+    __syncthreads();
+    const HaltonShared hs{sbase, soff, smagic, sdl, sarh, sarl, table_saddr};
     const uint64_t rows = i_end - i_begin, n = src.n;
     const uint64_t ntiles = (rows + 31) / 32;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -141,29 +145,17 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
         const uint64_t i = i_begin + (live ? r : rows - 1);
         const uint64_t pi = src.perm[i];
         // ---- P1: coordinates and terms
-        for (int d = warp; d < k; d += PF_WARPS) {
-            double pa, pb;
-            if (src.raw) {
-                pa = src.raw[i * (uint64_t)k + d];
-                pb = src.raw[(n + pi) * (uint64_t)k + d];
-            } else {
-                const uint32_t b = sbase[d];
-                const uint32_t ma = (uint32_t)(src.start + i), mb = (uint32_t)(src.start + n + pi);
-                if (b == 2u) {
-                    pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
-                    pb = (double)__brev(mb) * 2.3283064365386962890625e-10;
-                } else if (d < PF_AR_D0) {
-                    // table terms for the small bases (rows of <= 31 doubles: conflict-free or nearly so), multiply-only digit loop
-                    halton_pair<true>(ma, mb, b, smagic[d], sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pb);
-                } else {
-                    // computed terms: digit / b^(j+1) = fma(dd, rh, dd * rl), dd = 8 * digit (fused_impl.cuh: digit_step_arith)
-                    halton_pair<false>(ma, mb, b, smagic[d], sdl[d], 0u, sarh + (size_t)d * PF_AR_J, sarl + (size_t)d * PF_AR_J, pa, pb);
-                }
-            }
+        auto emit = [&](int d, double pa, double pb) {
             if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pb = __dadd_rn(__dmul_rn(pb, swr[d]), slb[d]); }
             else if (s.kind == VS_SCALE_POWER) { pa = __dmul_rn(slb[d], pow(swr[d], pa)); pb = __dmul_rn(slb[d], pow(swr[d], pb)); }
             TA[(size_t)d * 32 + lane] = f.term(d, pa);
             TB[(size_t)d * 32 + lane] = f.term(d, pb);
+        };
+        if (src.raw) {
+            for (int d = warp; d < k; d += PF_WARPS) emit(d, src.raw[i * (uint64_t)k + d], src.raw[(n + pi) * (uint64_t)k + d]);
+        } else {
+            // units of one table dimension or two computed-term dimensions, balanced over the warps (device.cuh: halton_schedule)
+            halton_units(warp, uwarp, k, (uint32_t)(src.start + i), (uint32_t)(src.start + n + pi), hs, emit);
         }
         __syncthreads();
         // ---- P2: four product chains, lane = row
@@ -203,7 +195,7 @@ static int launch_eval_pf(vs_ctx *c, int k, const SourceDev &src, const ScaleDev
     *done = false;
     const uint64_t rows = i_end - i_begin;
     if (rows == 0 || c->opt.no_pf_eval) return VS_OK;
-    if (!src.raw && (src.h.mode == VS_HALTON_HORNER || !src.h.arith_ok)) return VS_OK;
+    if (!src.raw && (src.h.mode == VS_HALTON_HORNER || !src.h.arith_ok || halton_unit_count(k) > HL_MAX_UNITS)) return VS_OK;
     uint32_t table_len = 0;
     if (!src.raw) {
         // the table prefix of the dimensions below PF_AR_D0 (terms are laid out dimension by dimension: b_d * ndigits_d each)
@@ -212,7 +204,7 @@ static int launch_eval_pf(vs_ctx *c, int k, const SourceDev &src, const ScaleDev
         for (int d = 0; d < k && d < PF_AR_D0; ++d) table_len += small_primes[d] * c->halton.ndigits[d];
         if (k <= PF_AR_D0) table_len = src.h.total_terms;
     }
-    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + 2 * (size_t)k + table_len + 2 * (size_t)k * 32 +
+    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + 2 * (size_t)k + HL_LIST_BYTES / 8 + table_len + 2 * (size_t)k * 32 +
                            4 * (size_t)(k + 1) * 32 + 2;
     const size_t smem = doubles * sizeof(double);
     if (smem > c->smem_optin) return VS_OK;

@@ -121,6 +121,7 @@ struct Options {
     std::string trace;          // VS_TRACE          file for CTA 0's clock stamps
     int gram_mma = -1;          // VS_GRAM_MMA       (-1 = default)
     int export_slow_gen = 0;    // VS_EXPORT_SLOW_GEN=1: generic digit loop in the bulk export kernel (comparison runs)
+    int export_smem_kb = 0;     // VS_EXPORT_SMEM_KB: request at least this much dynamic shared memory (L1 carve-out experiments)
     int export_copies = 0;      // VS_EXPORT_COPIES=1|2: store warps / tile copies of the bulk export kernel (0: by window shape)
     int gram_mma_gen = -1;      // VS_GRAM_GEN       0: register-tile kernel for l > 1 outputs / odd row counts
     int gram_st = 0, gram_rc = 0, gram_stages = 0, gram_hint = 0x989680, gram_debug = 0;
