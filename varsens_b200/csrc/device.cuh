@@ -116,6 +116,10 @@ __device__ __forceinline__ void halton_pair(uint32_t ma, uint32_t mb, uint32_t b
 // loop -- half the loop and branch overhead per dimension and twice the independent work per warp.  The trip counts are
 // the larger ones of the two dimensions: a general division step is exact for any index, and a position beyond a
 // dimension's last digit adds fma(0, rh, 0 * rl) = +0.0.
+#ifndef VS_HL_UNROLL
+#define VS_HL_UNROLL 1          // unroll factor of the four-chain loop (make exp EXTRA=-DVS_HL_UNROLL=2 for a comparison build)
+#endif
+constexpr int HL_UNROLL = VS_HL_UNROLL;
 __device__ __forceinline__ void halton_quad_arith(uint32_t ia, uint32_t ib, uint32_t b1, uint64_t magic1, const DimLoop dl1,
                                                   const double *__restrict__ rh1, const double *__restrict__ rl1, uint32_t b2,
                                                   uint64_t magic2, const DimLoop dl2, const double *__restrict__ rh2,
@@ -139,7 +143,7 @@ __device__ __forceinline__ void halton_quad_arith(uint32_t ia, uint32_t ib, uint
         pb2 = __dadd_rn(pb2, term(8u * (mb2 - qb2 * b2), h2, l2));
         ma1 = qa1; mb1 = qb1; ma2 = qa2; mb2 = qb2;
     }
-#pragma unroll 1
+#pragma unroll HL_UNROLL
     for (; j < nd; ++j) {
         const uint64_t wa1 = (uint64_t)ma1 * dl1.c32, wb1 = (uint64_t)mb1 * dl1.c32;
         const uint64_t wa2 = (uint64_t)ma2 * dl2.c32, wb2 = (uint64_t)mb2 * dl2.c32;

@@ -44,7 +44,7 @@ struct MmaGeom {
     int rc, pitch, nstage; // rows per chunk, doubles per staged column, ring depth
     int second;
     int sumu;              // position of super-tile (0,0) in the list: its warps also accumulate the shifted sums
-    unsigned char witem[16];   // consumer warp -> work item (super-tile of this pass * rs + row subset), 255 = idle
+    unsigned char witem[32];   // consumer warp -> work item (super-tile of this pass * rs + row subset), 255 = idle
     unsigned char ui[128], uj[128];   // super-tile list, heaviest first
     int hint;              // try_wait suspend-time hint, ns
     int debug;             // elimination experiments (VS_GRAM_DEBUG): 1 = no Gram update, 2 = no copies
@@ -161,8 +161,11 @@ __device__ __forceinline__ void mma_steps(double (&acc)[ST * ST][2], double (&sS
 constexpr int MMA_BAR_DOUBLES = 16;     // full[8] + empty[8]
 constexpr int MMA_MAX_STAGES = 8;
 
-template <int ST, bool MULTI, bool GUARD, bool GEN>   // MULTI: several super-tiles (ST = 4 or 2); otherwise one diagonal super-tile
-__global__ void __launch_bounds__(MULTI ? 512 : 384)
+// MULTI: several super-tiles (ST = 4 or 2); otherwise one diagonal super-tile.  The 2 x 2 form needs <= 64 registers, so a CTA
+// may hold 31 consumer warps: 28 super-tiles at k = 50 fit ONE pass over the data (15 warps needed two: 6.85 GB of DRAM reads
+// for 3.42 GB of values, ncu) and light configurations get three row subsets per super-tile.
+template <int ST, bool MULTI, bool GUARD, bool GEN>
+__global__ void __launch_bounds__(MULTI ? (ST == 2 ? 1024 : 512) : 384)
 gram_mma_kernel(MmaGeom g, uint64_t rows, const double *__restrict__ fvals, const double *__restrict__ shift,
                 double *__restrict__ blockpart) {
     extern __shared__ __align__(16) double smem[];
@@ -445,10 +448,20 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
     // warps sharing it) * that, or the bulk copies of the pass (~2 cycles per coordinate and 4-row step), whichever is larger.
     const bool multi = g.nb > 6;
     int ST = g.nb <= 2 ? 2 : g.nb == 3 ? 3 : g.nb == 4 ? 4 : 6;
-    const int maxw = multi ? 15 : 11;        // + 1 producer warp: 16 warps -> 128 registers per thread, 12 warps -> 168
+    // consumer warps (+ 1 producer warp): 12 warps -> 168 registers per thread, 16 -> 128; the 2 x 2 form also runs with 32
+    // warps (64 registers) -- used only where that turns two passes over the data into one (16..31 super-tiles: k = 50
+    // 2.24 -> 2.05 ms); elsewhere the 15-warp form measured faster (k = 30: 0.76 vs 0.79 ms, k = 100: 1.95 vs 2.17,
+    // l = 3 k = 20: 0.67 vs 0.87; tools/gram_probe.py).
+    auto maxw_of = [&](int st) {
+        if (!multi) return 11;
+        const int nsb = (g.nb + st - 1) / st, nunits = g.second ? nsb * (nsb + 1) / 2 : nsb;
+        const bool wide = st == 2 && nunits > 15 && nunits <= 31 && c->opt.gram_warps != 15;
+        return (wide || c->opt.gram_warps == 31) && st == 2 ? 31 : 15;
+    };
     if (multi) {
         double best = 0.0;
         for (int st : {4, 2}) {
+            const int maxw = maxw_of(st);
             const int nsb = (g.nb + st - 1) / st;
             const int nunits = g.second ? nsb * (nsb + 1) / 2 : nsb;
             const int upc = nunits < maxw ? nunits : maxw, passes = (nunits + upc - 1) / upc, rs = maxw / upc;
@@ -462,6 +475,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
     if (multi && (c->opt.gram_st == 2 || c->opt.gram_st == 4)) ST = c->opt.gram_st;                  // tuning switch (VS_GRAM_ST)
     if (multi && 2 * l > 8 * ST) ST = 4;                      // the shifted sums (coordinates < 2l) live in super-tile (0, 0)
     if (2 * l > 8 * ST) return VS_OK;
+    const int maxw = maxw_of(ST);
     const bool guard = multi || !g.second || g.nb != ST;
     g.nsb = (g.nb + ST - 1) / ST;
     g.nunits = g.second ? g.nsb * (g.nsb + 1) / 2 : g.nsb;
@@ -492,7 +506,7 @@ int launch_gram_mma(vs_ctx *c, int k, int l, uint64_t rows, const double *fvals,
         }
         int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
         if (g.warps % 4 == 3) load[3] = 1;                           // the producer warp shares sub-partition (warps % 4)
-        for (int w = 0; w < 16; ++w) g.witem[w] = 255;
+        for (int w = 0; w < 32; ++w) g.witem[w] = 255;
         for (int item = 0; item < g.upc * g.rs; ++item) {
             const int wt = units[item / g.rs].w;                     // pass 0 decides; later passes have the same shape or lighter
             int best = -1;
