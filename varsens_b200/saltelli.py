@@ -45,6 +45,29 @@ def _reference_permutation(n):
     return perm
 
 
+_perm_dev_cache = {}      # (n, device) -> int32 CUDA tensor holding the same permutation; a few entries, newest last
+
+
+def _device_permutation(perm, n, device):
+    """The permutation as a device-resident tensor of GPU `device`, uploaded once per (n, device): the order depends on n only,
+    so a repeated ``Varsens(functor, scaling, k, n)`` neither draws nor copies it again (64 MB over PCIe from pageable host
+    memory cost as much as the whole fused step at n = 2^24).  Falls back to the host array when torch has no CUDA."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return perm
+    except ImportError:
+        return perm
+    key = (int(n), int(device))
+    t = _perm_dev_cache.get(key)
+    if t is None:
+        while len(_perm_dev_cache) >= 4:
+            _perm_dev_cache.pop(next(iter(_perm_dev_cache)))
+        t = torch.tensor(perm.view(numpy.int32), device=torch.device("cuda", int(device)))
+        _perm_dev_cache[key] = t
+    return t
+
+
 class Sample(object):
     """Sample space definition plus the matrices M_1, M_2, N_j, N_nj (varsens/saltelli.py:13-250)."""
 
@@ -110,11 +133,17 @@ class Sample(object):
         """True if rows can be generated by the kernels (not a flattened-file sample)."""
         return self._explicit is None
 
+    def _perm_arg(self):
+        """The row permutation as the kernels take it: the device-resident copy of this GPU (cached per n)."""
+        if self._perm is None:
+            return None
+        return _device_permutation(self._perm, self.n, self.ctx.device)
+
     def flat_rows(self, row_begin, row_end, out=None):
         """Rows [row_begin,row_end) of flat(); `out` may be a CUDA torch tensor (stays on the GPU)."""
         if self._explicit is not None:
             return self._explicit_flat()[row_begin:row_end]
-        return self.ctx.sample_flat(self.k, self.n, self._perm, self.discard, self._scale, self._raw,
+        return self.ctx.sample_flat(self.k, self.n, self._perm_arg(), self.discard, self._scale, self._raw,
                                     row_begin, row_end, out)
 
     def _block(self, name):
@@ -330,7 +359,7 @@ class Objective(object):
 
     def _evaluate_functor(self):
         s = self.sample
-        v = s.ctx.eval_values(self.k, self.n, s._perm, self._functor.objective_id, self._functor.params(self.k),
+        v = s.ctx.eval_values(self.k, self.n, s._perm_arg(), self._functor.objective_id, self._functor.params(self.k),
                               s.discard, s._scale, s._raw)
         self._vals = numpy.ascontiguousarray(v.reshape(-1, 1))
 
@@ -448,4 +477,4 @@ class Varsens(object):
 
     def _fused(self, o, k, n, flags):
         s, f = o.sample, o._functor
-        return dist.fused_step(s.ctx, k, n, s._perm, f.objective_id, f.params(k), s.discard, s._scale, s._raw, flags)
+        return dist.fused_step(s.ctx, k, n, s._perm_arg(), f.objective_id, f.params(k), s.discard, s._scale, s._raw, flags)
