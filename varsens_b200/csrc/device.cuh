@@ -76,9 +76,12 @@ __device__ __forceinline__ DimLoop dim_loop(uint32_t b, uint64_t max_index) {
     return dl;
 }
 
-template <bool TABLE>
-__device__ __forceinline__ void halton_pair(uint32_t ma, uint32_t mb, uint32_t b, uint64_t magic, const DimLoop dl, uint32_t row,
-                                            const double *__restrict__ rh, const double *__restrict__ rl, double &pa, double &pb) {
+// NR row groups per lane: the lane's rows r, r + 32, ... advance together (2 NR chains per dimension) with the SAME
+// warp-uniform constants -- the per-dimension prologue is paid once for NR rows and the independent work per warp grows NR-fold.
+template <bool TABLE, int NR>
+__device__ __forceinline__ void halton_pair(const uint32_t (&ia)[NR], const uint32_t (&ib)[NR], uint32_t b, uint64_t magic,
+                                            const DimLoop dl, uint32_t row, const double *__restrict__ rh,
+                                            const double *__restrict__ rl, double (&pa)[NR], double (&pb)[NR]) {
     auto term = [&](uint32_t off8, int j) -> double {
         if constexpr (TABLE) {
             double t;
@@ -89,71 +92,86 @@ __device__ __forceinline__ void halton_pair(uint32_t ma, uint32_t mb, uint32_t b
             return __fma_rn(dd, rh[j], __dmul_rn(dd, rl[j]));
         }
     };
-    pa = 0.0;
-    pb = 0.0;
+    uint32_t ma[NR], mb[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { ma[r] = ia[r]; mb[r] = ib[r]; pa[r] = 0.0; pb[r] = 0.0; }
     int j = 0;
 #pragma unroll 1
     for (; j < dl.jg; ++j) {                                  // usually 0 or 1 trips
-        const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma, magic), qb = (uint32_t)__umul64hi((uint64_t)mb, magic);
-        pa = __dadd_rn(pa, term(8u * (ma - qa * b), j));
-        pb = __dadd_rn(pb, term(8u * (mb - qb * b), j));
-        ma = qa;
-        mb = qb;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t qa = (uint32_t)__umul64hi((uint64_t)ma[r], magic), qb = (uint32_t)__umul64hi((uint64_t)mb[r], magic);
+            pa[r] = __dadd_rn(pa[r], term(8u * (ma[r] - qa * b), j));
+            pb[r] = __dadd_rn(pb[r], term(8u * (mb[r] - qb * b), j));
+            ma[r] = qa;
+            mb[r] = qb;
+        }
         if constexpr (TABLE) row += dl.b8;
     }
-#pragma unroll 2
+#pragma unroll(NR == 1 ? 2 : 1)
     for (; j < dl.nd; ++j) {
-        const uint64_t wa = (uint64_t)ma * dl.c32, wb = (uint64_t)mb * dl.c32;
-        ma = (uint32_t)(wa >> 32);
-        mb = (uint32_t)(wb >> 32);
-        pa = __dadd_rn(pa, term(__umulhi((uint32_t)wa, dl.b8), j));
-        pb = __dadd_rn(pb, term(__umulhi((uint32_t)wb, dl.b8), j));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint64_t wa = (uint64_t)ma[r] * dl.c32, wb = (uint64_t)mb[r] * dl.c32;
+            ma[r] = (uint32_t)(wa >> 32);
+            mb[r] = (uint32_t)(wb >> 32);
+            pa[r] = __dadd_rn(pa[r], term(__umulhi((uint32_t)wa, dl.b8), j));
+            pb[r] = __dadd_rn(pb[r], term(__umulhi((uint32_t)wb, dl.b8), j));
+        }
         if constexpr (TABLE) row += dl.b8;
     }
 }
 
-// Two dimensions with computed terms at once: four chains (A and B index of the row in dimensions d1 and d2) share one
+// Two dimensions with computed terms at once: 4 NR chains (A and B index of NR rows in dimensions d1 and d2) share one
 // loop -- half the loop and branch overhead per dimension and twice the independent work per warp.  The trip counts are
 // the larger ones of the two dimensions: a general division step is exact for any index, and a position beyond a
 // dimension's last digit adds fma(0, rh, 0 * rl) = +0.0.
-#ifndef VS_HL_UNROLL
-#define VS_HL_UNROLL 1          // unroll factor of the four-chain loop (make exp EXTRA=-DVS_HL_UNROLL=2 for a comparison build)
-#endif
-constexpr int HL_UNROLL = VS_HL_UNROLL;
-__device__ __forceinline__ void halton_quad_arith(uint32_t ia, uint32_t ib, uint32_t b1, uint64_t magic1, const DimLoop dl1,
-                                                  const double *__restrict__ rh1, const double *__restrict__ rl1, uint32_t b2,
-                                                  uint64_t magic2, const DimLoop dl2, const double *__restrict__ rh2,
-                                                  const double *__restrict__ rl2, double &pa1, double &pb1, double &pa2, double &pb2) {
+template <int NR>
+__device__ __forceinline__ void halton_quad_arith(const uint32_t (&ia)[NR], const uint32_t (&ib)[NR], uint32_t b1, uint64_t magic1,
+                                                  const DimLoop dl1, const double *__restrict__ rh1, const double *__restrict__ rl1,
+                                                  uint32_t b2, uint64_t magic2, const DimLoop dl2, const double *__restrict__ rh2,
+                                                  const double *__restrict__ rl2, double (&pa1)[NR], double (&pb1)[NR],
+                                                  double (&pa2)[NR], double (&pb2)[NR]) {
     auto term = [](uint32_t off8, double rh, double rl) -> double {
         const double dd = __dadd_rn(__hiloint2double(0x43300000, (int)off8), -4503599627370496.0);       // 2^52 + off8, exact
         return __fma_rn(dd, rh, __dmul_rn(dd, rl));
     };
-    uint32_t ma1 = ia, mb1 = ib, ma2 = ia, mb2 = ib;
-    pa1 = 0.0; pb1 = 0.0; pa2 = 0.0; pb2 = 0.0;
+    uint32_t ma1[NR], mb1[NR], ma2[NR], mb2[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        ma1[r] = ia[r]; mb1[r] = ib[r]; ma2[r] = ia[r]; mb2[r] = ib[r];
+        pa1[r] = 0.0; pb1[r] = 0.0; pa2[r] = 0.0; pb2[r] = 0.0;
+    }
     const int jg = max(dl1.jg, dl2.jg), nd = max(dl1.nd, dl2.nd);
     int j = 0;
 #pragma unroll 1
     for (; j < jg; ++j) {                                     // usually 0 or 1 trips
-        const uint32_t qa1 = (uint32_t)__umul64hi((uint64_t)ma1, magic1), qb1 = (uint32_t)__umul64hi((uint64_t)mb1, magic1);
-        const uint32_t qa2 = (uint32_t)__umul64hi((uint64_t)ma2, magic2), qb2 = (uint32_t)__umul64hi((uint64_t)mb2, magic2);
         const double h1 = rh1[j], l1 = rl1[j], h2 = rh2[j], l2 = rl2[j];
-        pa1 = __dadd_rn(pa1, term(8u * (ma1 - qa1 * b1), h1, l1));
-        pb1 = __dadd_rn(pb1, term(8u * (mb1 - qb1 * b1), h1, l1));
-        pa2 = __dadd_rn(pa2, term(8u * (ma2 - qa2 * b2), h2, l2));
-        pb2 = __dadd_rn(pb2, term(8u * (mb2 - qb2 * b2), h2, l2));
-        ma1 = qa1; mb1 = qb1; ma2 = qa2; mb2 = qb2;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint32_t qa1 = (uint32_t)__umul64hi((uint64_t)ma1[r], magic1), qb1 = (uint32_t)__umul64hi((uint64_t)mb1[r], magic1);
+            const uint32_t qa2 = (uint32_t)__umul64hi((uint64_t)ma2[r], magic2), qb2 = (uint32_t)__umul64hi((uint64_t)mb2[r], magic2);
+            pa1[r] = __dadd_rn(pa1[r], term(8u * (ma1[r] - qa1 * b1), h1, l1));
+            pb1[r] = __dadd_rn(pb1[r], term(8u * (mb1[r] - qb1 * b1), h1, l1));
+            pa2[r] = __dadd_rn(pa2[r], term(8u * (ma2[r] - qa2 * b2), h2, l2));
+            pb2[r] = __dadd_rn(pb2[r], term(8u * (mb2[r] - qb2 * b2), h2, l2));
+            ma1[r] = qa1; mb1[r] = qb1; ma2[r] = qa2; mb2[r] = qb2;
+        }
     }
-#pragma unroll HL_UNROLL
+#pragma unroll 1
     for (; j < nd; ++j) {
-        const uint64_t wa1 = (uint64_t)ma1 * dl1.c32, wb1 = (uint64_t)mb1 * dl1.c32;
-        const uint64_t wa2 = (uint64_t)ma2 * dl2.c32, wb2 = (uint64_t)mb2 * dl2.c32;
         const double h1 = rh1[j], l1 = rl1[j], h2 = rh2[j], l2 = rl2[j];
-        ma1 = (uint32_t)(wa1 >> 32); mb1 = (uint32_t)(wb1 >> 32);
-        ma2 = (uint32_t)(wa2 >> 32); mb2 = (uint32_t)(wb2 >> 32);
-        pa1 = __dadd_rn(pa1, term(__umulhi((uint32_t)wa1, dl1.b8), h1, l1));
-        pb1 = __dadd_rn(pb1, term(__umulhi((uint32_t)wb1, dl1.b8), h1, l1));
-        pa2 = __dadd_rn(pa2, term(__umulhi((uint32_t)wa2, dl2.b8), h2, l2));
-        pb2 = __dadd_rn(pb2, term(__umulhi((uint32_t)wb2, dl2.b8), h2, l2));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const uint64_t wa1 = (uint64_t)ma1[r] * dl1.c32, wb1 = (uint64_t)mb1[r] * dl1.c32;
+            const uint64_t wa2 = (uint64_t)ma2[r] * dl2.c32, wb2 = (uint64_t)mb2[r] * dl2.c32;
+            ma1[r] = (uint32_t)(wa1 >> 32); mb1[r] = (uint32_t)(wb1 >> 32);
+            ma2[r] = (uint32_t)(wa2 >> 32); mb2[r] = (uint32_t)(wb2 >> 32);
+            pa1[r] = __dadd_rn(pa1[r], term(__umulhi((uint32_t)wa1, dl1.b8), h1, l1));
+            pb1[r] = __dadd_rn(pb1[r], term(__umulhi((uint32_t)wb1, dl1.b8), h1, l1));
+            pa2[r] = __dadd_rn(pa2[r], term(__umulhi((uint32_t)wa2, dl2.b8), h2, l2));
+            pb2[r] = __dadd_rn(pb2[r], term(__umulhi((uint32_t)wb2, dl2.b8), h2, l2));
+        }
     }
 }
 
@@ -171,7 +189,7 @@ struct HaltonShared {
 // The unscaled coordinates of one row pair (A index ia, B index ib), lane = row, distributed over the warps of a team by
 // UNITS: unit u < min(k, HL_D0) is the single dimension u (base 2: a bit reversal; bases 3..31: table terms), the units after
 // those are PAIRS of computed-term dimensions (HL_D0 + 2p, HL_D0 + 2p + 1).  ulist[w * HL_MAXQ + q] is the q-th unit of warp w,
-// 255 ends the list (halton_schedule); emit(d, pa, pb) receives every coordinate once.  All branches are warp-uniform.
+// 255 ends the list (halton_schedule); emit receives every coordinate once.  All branches are warp-uniform.
 constexpr int HL_MAXQ = 32;            // units per warp at most
 constexpr int HL_MAX_UNITS = 160;      // k <= 309: at most 20 units per warp on average with 8 warps
 constexpr int HL_LIST_BYTES = 16 * HL_MAXQ;   // up to 16 warps
@@ -212,9 +230,10 @@ __device__ inline void halton_schedule(int k, int nw, const DimLoop *dl, unsigne
     if (nunits > 0) place(0, 1.0f);                          // dimension 0: base 2, a bit reversal
 }
 
-template <class Emit>
-__device__ __forceinline__ void halton_units(int w, const unsigned char *__restrict__ ulist, int k, uint32_t ia, uint32_t ib,
-                                             const HaltonShared &hs, Emit &&emit) {
+// emit(d, r, pa, pb): coordinate d of the lane's r-th row (A point, B point).
+template <int NR, class Emit>
+__device__ __forceinline__ void halton_units(int w, const unsigned char *__restrict__ ulist, int k, const uint32_t (&ia)[NR],
+                                             const uint32_t (&ib)[NR], const HaltonShared &hs, Emit &&emit) {
     const int nsmall = k < HL_D0 ? k : HL_D0;
     const uint32_t *wl = reinterpret_cast<const uint32_t *>(ulist + w * HL_MAXQ);      // four units per load
     uint32_t pack = wl[0];
@@ -225,27 +244,33 @@ __device__ __forceinline__ void halton_units(int w, const unsigned char *__restr
         if (u == 255) break;
         if (u < nsmall) {
             const uint32_t b = hs.base[u];
-            double pa, pb;
+            double pa[NR], pb[NR];
             if (b == 2u) {
-                pa = (double)__brev(ia) * 2.3283064365386962890625e-10;
-                pb = (double)__brev(ib) * 2.3283064365386962890625e-10;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    pa[r] = (double)__brev(ia[r]) * 2.3283064365386962890625e-10;
+                    pb[r] = (double)__brev(ib[r]) * 2.3283064365386962890625e-10;
+                }
             } else {
-                halton_pair<true>(ia, ib, b, hs.magic[u], hs.dl[u], hs.table_saddr + 8u * hs.off[u], nullptr, nullptr, pa, pb);
+                halton_pair<true, NR>(ia, ib, b, hs.magic[u], hs.dl[u], hs.table_saddr + 8u * hs.off[u], nullptr, nullptr, pa, pb);
             }
-            emit(u, pa, pb);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) emit(u, r, pa[r], pb[r]);
         } else {
             const int d1 = HL_D0 + 2 * (u - nsmall), d2 = d1 + 1;
             if (d2 < k) {
-                double pa1, pb1, pa2, pb2;
-                halton_quad_arith(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J,
-                                  hs.base[d2], hs.magic[d2], hs.dl[d2], hs.arh + (size_t)d2 * HL_J, hs.arl + (size_t)d2 * HL_J, pa1, pb1,
-                                  pa2, pb2);
-                emit(d1, pa1, pb1);
-                emit(d2, pa2, pb2);
+                double pa1[NR], pb1[NR], pa2[NR], pb2[NR];
+                halton_quad_arith<NR>(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J,
+                                      hs.base[d2], hs.magic[d2], hs.dl[d2], hs.arh + (size_t)d2 * HL_J, hs.arl + (size_t)d2 * HL_J, pa1,
+                                      pb1, pa2, pb2);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) { emit(d1, r, pa1[r], pb1[r]); emit(d2, r, pa2[r], pb2[r]); }
             } else {
-                double pa, pb;
-                halton_pair<false>(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], 0u, hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J, pa, pb);
-                emit(d1, pa, pb);
+                double pa[NR], pb[NR];
+                halton_pair<false, NR>(ia, ib, hs.base[d1], hs.magic[d1], hs.dl[d1], 0u, hs.arh + (size_t)d1 * HL_J, hs.arl + (size_t)d1 * HL_J,
+                                       pa, pb);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) emit(d1, r, pa[r], pb[r]);
             }
         }
     }

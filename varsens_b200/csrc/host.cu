@@ -74,6 +74,7 @@ void load_options(Options &o) {
     o.export_smem_kb = env_int("VS_EXPORT_SMEM_KB", 0);
     o.gram_st = env_int("VS_GRAM_ST", 0);
     o.gram_warps = env_int("VS_GRAM_WARPS", 0);
+    o.pf_rows = env_int("VS_PF_ROWS", 0);
     o.gram_rc = env_int("VS_GRAM_RC", 0);
     o.gram_stages = env_int("VS_GRAM_STAGES", 0);
     o.gram_hint = env_int("VS_GRAM_HINT", 0x989680);

@@ -300,7 +300,8 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
             };
             if (g.fast == 1) {
                 // units of one table dimension or two computed-term dimensions, balanced over the generator warps (halton_schedule)
-                halton_units(gw, uwarp, k, (uint32_t)(src.start + i), (uint32_t)(src.start + n + pi), hs, emit);
+                const uint32_t ia[1] = {(uint32_t)(src.start + i)}, ib[1] = {(uint32_t)(src.start + n + pi)};
+                halton_units<1>(gw, uwarp, k, ia, ib, hs, [&](int d, int, double pa, double pbv) { emit(d, pa, pbv); });
             } else if (g.fast == 2) {
                 // comparison form (VS_EXPORT_SLOW_GEN=2): one dimension at a time, round-robin over the generator warps
                 for (int d = gw; d < k; d += EX_GEN / 32) {
@@ -309,8 +310,14 @@ sample_flat_bulk_kernel(ExportGeom g, SourceDev src, ScaleDev s, double *__restr
                     if (b == 2u) {
                         pa = (double)__brev(ma) * 2.3283064365386962890625e-10;
                         pbv = (double)__brev(mb) * 2.3283064365386962890625e-10;
-                    } else if (d < EX_AR_D0) halton_pair<true>(ma, mb, b, smagic[d], sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, pa, pbv);
-                    else halton_pair<false>(ma, mb, b, smagic[d], sdl[d], 0u, sarh + (size_t)d * EX_AR_J, sarl + (size_t)d * EX_AR_J, pa, pbv);
+                    } else {
+                        const uint32_t ia[1] = {ma}, ib[1] = {mb};
+                        double qa[1], qb[1];
+                        if (d < EX_AR_D0) halton_pair<true, 1>(ia, ib, b, smagic[d], sdl[d], table_saddr + 8u * soff[d], nullptr, nullptr, qa, qb);
+                        else halton_pair<false, 1>(ia, ib, b, smagic[d], sdl[d], 0u, sarh + (size_t)d * EX_AR_J, sarl + (size_t)d * EX_AR_J, qa, qb);
+                        pa = qa[0];
+                        pbv = qb[0];
+                    }
                     emit(d, pa, pbv);
                 }
             } else {

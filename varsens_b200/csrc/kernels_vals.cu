@@ -99,13 +99,18 @@ __global__ void eval_values_kernel(int k, int pts_per_chunk, SourceDev src, Scal
 // this phase to ~1.5 (tools/bench_configs.py).  The values are the same products associated differently (prefix * term *
 // suffix instead of left to right): <= 2 ulp from F::operator(), far inside the 1e-10 contract on the indices.
 // ---------------------------------------------------------------------------------------------
-constexpr int PF_AR_D0 = HL_D0, PF_AR_J = HL_J, PF_WARPS = 8;
+constexpr int PF_AR_D0 = HL_D0, PF_AR_J = HL_J;
 
-template <class F>
-__global__ void __launch_bounds__(PF_WARPS * 32, 2)
+// NR row groups per lane: a CTA tile has 32 NR rows and 8 NR warps.  NR = 2 (one CTA of 16 warps per SM instead of two of 8)
+// keeps the rows in flight per SM, doubles the independent digit chains per warp and halves the per-dimension prologue per row
+// in P1 -- and measured slower (see launch_eval_pf), so NR = 1 is the default and NR = 2 a switch.
+template <class F, int NR>
+__global__ void __launch_bounds__(256 * NR, NR == 1 ? 2 : 1)
 eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, uint64_t i_end, uint32_t table_len, double *__restrict__ fvals) {
+    constexpr int ROWS = 32 * NR, WARPS = 8 * NR;
     extern __shared__ __align__(16) double smem[];
-    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | dl[k] | ulist[16][32] (u8) | table[table_len] | TA TB [k][32] | PA PB SA SB [k+1][32]
+    // layout: base[k] off[k] (u32) | magic[k] (u64) | lb wr [k] | arh arl [k][7] | dl[k] | ulist[16][32] (u8) | table[table_len] |
+    //         TA TB [k][ROWS] | PA PB SA SB [k+1][ROWS]
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem);
     uint32_t *soff = sbase + k;
     uint64_t *smagic = reinterpret_cast<uint64_t *>(smem + ((2 * k + 1) / 2));
@@ -113,11 +118,11 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
     double *swr = slb + k;
     double *sarh = swr + k, *sarl = sarh + (size_t)k * PF_AR_J;
     DimLoop *sdl = reinterpret_cast<DimLoop *>(sarl + (size_t)k * PF_AR_J);       // 16 bytes per dimension
-    unsigned char *uwarp = reinterpret_cast<unsigned char *>(sdl + k);            // [warp][HL_MAXQ]: the units of every warp
+    unsigned char *ulist = reinterpret_cast<unsigned char *>(sdl + k);            // [warp][HL_MAXQ]: the units of every warp
     double *table = reinterpret_cast<double *>(sdl + k) + HL_LIST_BYTES / 8;
     const uint32_t table_saddr = (uint32_t)__cvta_generic_to_shared(table);
-    double *TA = table + table_len, *TB = TA + (size_t)k * 32;
-    double *PA = TB + (size_t)k * 32, *PB = PA + (size_t)(k + 1) * 32, *SA = PB + (size_t)(k + 1) * 32, *SB = SA + (size_t)(k + 1) * 32;
+    double *TA = table + table_len, *TB = TA + (size_t)k * ROWS;
+    double *PA = TB + (size_t)k * ROWS, *PB = PA + (size_t)(k + 1) * ROWS, *SA = PB + (size_t)(k + 1) * ROWS, *SB = SA + (size_t)(k + 1) * ROWS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (!src.raw) {
         for (int d = tid; d < k; d += blockDim.x) {
@@ -134,59 +139,105 @@ eval_values_pf_kernel(int k, SourceDev src, ScaleDev s, F f, uint64_t i_begin, u
         swr[d] = s.kind != VS_SCALE_IDENTITY ? s.wr[d] : 1.0;
     }
     __syncthreads();
-    if (!src.raw && tid == 0) halton_schedule(k, PF_WARPS, sdl, uwarp);
+    if (!src.raw && tid == 0) halton_schedule(k, WARPS, sdl, ulist);
     __syncthreads();
     const HaltonShared hs{sbase, soff, smagic, sdl, sarh, sarl, table_saddr};
     const uint64_t rows = i_end - i_begin, n = src.n;
-    const uint64_t ntiles = (rows + 31) / 32;
+    const uint64_t ntiles = (rows + ROWS - 1) / ROWS;
+    // base row of the lane's r-th row of a tile (clamped: the last tile may be ragged) and its permutation entry; the entry of
+    // the NEXT tile is requested before P1 of the current one, so its DRAM latency (7 % of the stall samples when it was
+    // loaded at the top of the loop, profiles/r02_evalpf_sass_profile_final.txt) is hidden behind a whole tile of work
+    auto base_row = [&](uint64_t tile, int r) {
+        const uint64_t q = tile * ROWS + 32 * r + lane;
+        return i_begin + (q < rows ? q : rows - 1);
+    };
+    uint64_t pi_next[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) pi_next[r] = blockIdx.x < ntiles ? src.perm[base_row(blockIdx.x, r)] : 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t r = tile * 32 + lane;
-        const bool live = r < rows;
-        const uint64_t i = i_begin + (live ? r : rows - 1);
-        const uint64_t pi = src.perm[i];
+        // the lane's NR rows: tile * ROWS + 32 r + lane
+        uint64_t rr[NR], ii[NR], pi[NR];
+        bool live[NR];
+        uint32_t ia[NR], ib[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            rr[r] = tile * ROWS + 32 * r + lane;
+            live[r] = rr[r] < rows;
+            ii[r] = base_row(tile, r);
+            pi[r] = pi_next[r];
+            ia[r] = (uint32_t)(src.start + ii[r]);
+            ib[r] = (uint32_t)(src.start + n + pi[r]);
+        }
+        if (tile + gridDim.x < ntiles) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) pi_next[r] = src.perm[base_row(tile + gridDim.x, r)];
+        }
         // ---- P1: coordinates and terms
-        auto emit = [&](int d, double pa, double pb) {
+        auto emit = [&](int d, int r, double pa, double pb) {
             if (s.kind == VS_SCALE_LINEAR) { pa = __dadd_rn(__dmul_rn(pa, swr[d]), slb[d]); pb = __dadd_rn(__dmul_rn(pb, swr[d]), slb[d]); }
             else if (s.kind == VS_SCALE_POWER) { pa = __dmul_rn(slb[d], pow(swr[d], pa)); pb = __dmul_rn(slb[d], pow(swr[d], pb)); }
-            TA[(size_t)d * 32 + lane] = f.term(d, pa);
-            TB[(size_t)d * 32 + lane] = f.term(d, pb);
+            TA[(size_t)d * ROWS + 32 * r + lane] = f.term(d, pa);
+            TB[(size_t)d * ROWS + 32 * r + lane] = f.term(d, pb);
         };
         if (src.raw) {
-            for (int d = warp; d < k; d += PF_WARPS) emit(d, src.raw[i * (uint64_t)k + d], src.raw[(n + pi) * (uint64_t)k + d]);
+            for (int d = warp; d < k; d += WARPS)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) emit(d, r, src.raw[ii[r] * (uint64_t)k + d], src.raw[(n + pi[r]) * (uint64_t)k + d]);
         } else {
             // units of one table dimension or two computed-term dimensions, balanced over the warps (device.cuh: halton_schedule)
-            halton_units(warp, uwarp, k, (uint32_t)(src.start + i), (uint32_t)(src.start + n + pi), hs, emit);
+            halton_units<NR>(warp, ulist, k, ia, ib, hs, emit);
         }
         __syncthreads();
-        // ---- P2: four product chains, lane = row
-        if (warp < 4) {
-            const double *Tm = (warp & 1) ? TB : TA;
-            if (warp < 2) {
-                double *P = warp ? PB : PA;
+        // ---- P2: four product chains per row group, lane = row
+        if (warp < 4 * NR) {
+            const int rg = warp >> 2, ch = warp & 3, col = 32 * rg + lane;
+            const double *Tm = (ch & 1) ? TB : TA;
+            if (ch < 2) {
+                double *P = ch ? PB : PA;
                 double p = 1.0;
-                P[lane] = p;
-                for (int c = 0; c < k; ++c) { p *= Tm[(size_t)c * 32 + lane]; P[(size_t)(c + 1) * 32 + lane] = p; }
+                P[col] = p;
+                for (int c = 0; c < k; ++c) { p *= Tm[(size_t)c * ROWS + col]; P[(size_t)(c + 1) * ROWS + col] = p; }
             } else {
-                double *S = (warp & 1) ? SB : SA;
+                double *S = (ch & 1) ? SB : SA;
                 double p = 1.0;
-                S[(size_t)k * 32 + lane] = p;
-                for (int c = k - 1; c >= 0; --c) { p *= Tm[(size_t)c * 32 + lane]; S[(size_t)c * 32 + lane] = p; }
+                S[(size_t)k * ROWS + col] = p;
+                for (int c = k - 1; c >= 0; --c) { p *= Tm[(size_t)c * ROWS + col]; S[(size_t)c * ROWS + col] = p; }
             }
         }
         __syncthreads();
         // ---- P3: the 2 + 2k values of every row
-        if (live) {
-            if (warp == 0) fvals[r] = PA[(size_t)k * 32 + lane];                                   // f(M_1[i])
-            if (warp == 1) fvals[rows + r] = PB[(size_t)k * 32 + lane];                            // f(M_2[i])
-            for (int j = warp; j < k; j += PF_WARPS) {
-                const double vj = PB[(size_t)j * 32 + lane] * TA[(size_t)j * 32 + lane] * SB[(size_t)(j + 1) * 32 + lane];   // M_2 with column j from M_1
-                const double vn = PA[(size_t)j * 32 + lane] * TB[(size_t)j * 32 + lane] * SA[(size_t)(j + 1) * 32 + lane];   // M_1 with column j from M_2
-                fvals[(uint64_t)(2 + j) * rows + r] = vj;
-                fvals[(uint64_t)(2 + k + j) * rows + r] = vn;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (!live[r]) continue;
+            const int col = 32 * r + lane;
+            const uint64_t ro = rr[r];
+            if (warp == 0) fvals[ro] = PA[(size_t)k * ROWS + col];                                  // f(M_1[i])
+            if (warp == 1) fvals[rows + ro] = PB[(size_t)k * ROWS + col];                           // f(M_2[i])
+            for (int j = warp; j < k; j += WARPS) {
+                const double vj = PB[(size_t)j * ROWS + col] * TA[(size_t)j * ROWS + col] * SB[(size_t)(j + 1) * ROWS + col];   // M_2 with column j from M_1
+                const double vn = PA[(size_t)j * ROWS + col] * TB[(size_t)j * ROWS + col] * SA[(size_t)(j + 1) * ROWS + col];   // M_1 with column j from M_2
+                fvals[(uint64_t)(2 + j) * rows + ro] = vj;
+                fvals[(uint64_t)(2 + k + j) * rows + ro] = vn;
             }
         }
         __syncthreads();
     }
+}
+
+template <class F, int NR>
+static int launch_eval_pf_t(vs_ctx *c, int k, const SourceDev &src, const ScaleDev &s, const F &f, uint64_t i_begin, uint64_t i_end,
+                            uint32_t table_len, size_t smem, double *fvals) {
+    const uint64_t rows = i_end - i_begin;
+    VS_CUDA(cudaFuncSetAttribute(eval_values_pf_kernel<F, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t ntiles = (rows + 32 * NR - 1) / (32 * NR);
+    const int per_sm = (NR == 1 && smem * 2 + 2048 <= c->smem_optin) ? 2 : 1;
+    const unsigned grid = (unsigned)(ntiles < (uint64_t)(per_sm * c->sm_count) ? ntiles : (uint64_t)(per_sm * c->sm_count));
+    time_begin(c);
+    eval_values_pf_kernel<F, NR><<<grid, 256 * NR, smem, c->stream>>>(k, src, s, f, i_begin, i_end, table_len, fvals);
+    time_end(c);
+    c->launches++;
+    VS_CUDA(cudaGetLastError());
+    return VS_OK;
 }
 
 template <class F>
@@ -204,19 +255,18 @@ static int launch_eval_pf(vs_ctx *c, int k, const SourceDev &src, const ScaleDev
         for (int d = 0; d < k && d < PF_AR_D0; ++d) table_len += small_primes[d] * c->halton.ndigits[d];
         if (k <= PF_AR_D0) table_len = src.h.total_terms;
     }
-    const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + 2 * (size_t)k + HL_LIST_BYTES / 8 + table_len + 2 * (size_t)k * 32 +
-                           4 * (size_t)(k + 1) * 32 + 2;
-    const size_t smem = doubles * sizeof(double);
+    auto smem_of = [&](int nr) {
+        const size_t doubles = (size_t)(2 * k + 1) / 2 + (size_t)k + 2 * (size_t)k + 2 * (size_t)k * PF_AR_J + 2 * (size_t)k + HL_LIST_BYTES / 8 +
+                               table_len + 2 * (size_t)k * 32 * nr + 4 * (size_t)(k + 1) * 32 * nr + 2;
+        return doubles * sizeof(double);
+    };
+    // VS_PF_ROWS=64: two row groups per lane (64-row tiles, one CTA of 16 warps per SM).  Measured SLOWER at C4 (3.07 vs 2.76 ms):
+    // twice the independent chains per warp do not make up for losing the second CTA whose phases interleave with the first.
+    const bool two = c->opt.pf_rows == 64 && smem_of(2) <= c->smem_optin && rows >= 64ull * c->sm_count;
+    const size_t smem = smem_of(two ? 2 : 1);
     if (smem > c->smem_optin) return VS_OK;
-    VS_CUDA(cudaFuncSetAttribute(eval_values_pf_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t ntiles = (rows + 31) / 32;
-    const int per_sm = smem * 2 + 2048 <= c->smem_optin ? 2 : 1;
-    const unsigned grid = (unsigned)(ntiles < (uint64_t)(per_sm * c->sm_count) ? ntiles : (uint64_t)(per_sm * c->sm_count));
-    time_begin(c);
-    eval_values_pf_kernel<F><<<grid, PF_WARPS * 32, smem, c->stream>>>(k, src, s, f, i_begin, i_end, table_len, fvals);
-    time_end(c);
-    c->launches++;
-    VS_CUDA(cudaGetLastError());
+    if (two) VS_TRY((launch_eval_pf_t<F, 2>(c, k, src, s, f, i_begin, i_end, table_len, smem, fvals)));
+    else VS_TRY((launch_eval_pf_t<F, 1>(c, k, src, s, f, i_begin, i_end, table_len, smem, fvals)));
     *done = true;
     return VS_OK;
 }
