@@ -19,6 +19,11 @@
  *  - everything is IEEE fp64; indices are uint64 in the ABI (Halton index of any generated point
  *    must stay below 2^32: VS_ERR_RANGE otherwise).
  *  - there is NO CPU fallback: without a CUDA device vs_ctx_create fails with VS_ERR_CUDA.
+ *  - limits (checked, never silent): 1 <= k <= 4096 for the generators, export mode and the estimators; vs_eval_values and
+ *    the two-phase route of vs_fused_partials / vs_run_fused need the 2k coordinates of 32 rows in shared memory
+ *    (k <= 453, VS_ERR_UNSUPPORTED beyond); the one-kernel fused route covers 2 <= k <= 20, other k take the two-phase
+ *    route inside the same calls; 1 <= l <= 64 outputs per evaluation (VS_ERR_ARG beyond: the reference has no such limit,
+ *    split the outputs into groups if the cross-output blocks of sens_2 are not needed).
  */
 #ifndef VARSENS_B200_H
 #define VARSENS_B200_H
