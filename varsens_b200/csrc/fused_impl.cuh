@@ -1338,14 +1338,17 @@ __global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) 
 // kernel variant (VS_FUSED_VARIANT overrides; see DESIGN.md "fused kernel variants"):
 //   1 = single-role warps, register-tile Gram (also the first-order-only kernel; separate shift / scatter launches)
 //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp     (one launch per step)
-// default: 6, except k >= 20 where the 12-warp form (168 registers per thread, no spills) wins since the paired layout
-// lightened the S-warps (n = 2^24: 4.79 vs 5.06 ms; k <= 18: variant 6 is 1-13 % faster, tools/variant_sweep.py)
+// default: 6 (k <= 18: 1-13 % faster than 5, tools/variant_sweep.py).  At k >= 20 the 12-warp form (168 registers per thread, no
+// spills) was the faster one while generation was table-bound (n = 2^24: 4.79 vs 5.06 ms); since the PTX digit step and the
+// computed terms it is the other way round for the generic functor -- k = 20: 4.45 vs 4.51 ms per step at n = 2^24, 0.587 vs
+// 0.598 ms at n = 2^21 (the per-rank rows of an 8-GPU run), same-box A/B -- and only the separable shortcut still prefers 5
+// (3.02 vs 3.21 ms).
 template <int K>
-static int fused_variant_for(const vs_ctx *c, bool second) {
+static int fused_variant_for(const vs_ctx *c, bool second, bool separable = false) {
     if (!second) return 1;
     const int v = c->opt.fused_variant;
     if (v == 1 || v == 5 || v == 6) return v;
-    return K >= 20 ? 5 : 6;
+    return (K >= 20 && separable) ? 5 : 6;
 }
 
 template <int K, class F, bool SECOND, bool SEPARABLE>
@@ -1361,7 +1364,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
-    const int variant = fused_variant_for<K>(c, SECOND);
+    const int variant = fused_variant_for<K>(c, SECOND, SEPARABLE);
     *finalized = false;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
@@ -1565,7 +1568,7 @@ static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const 
 // The one-launch step (estimators / peer exchange / chunk flags in the kernel's tail) exists for the warp-specialised variants.
 template <int K>
 static bool tail_supported_k(const vs_ctx *c, int flags) {
-    const int v = fused_variant_for<K>(c, (flags & VS_FLAG_SECOND_ORDER) != 0);
+    const int v = fused_variant_for<K>(c, (flags & VS_FLAG_SECOND_ORDER) != 0, (flags & VS_FLAG_SEPARABLE) != 0);
     return v == 5 || v == 6;
 }
 
