@@ -333,9 +333,10 @@ def run_gpu(args, rank, world):
             t = json.load(fh)
         traffic = float(t["dram_bytes"]) * rows_rank0 / float(t["rows"])
         traffic_src = "profiles/%s (ncu --set full, %s, n=%d)" % (t["file"], t["kernel"], t["rows"])
+    # the library's default at k = 20: three E-warps per S-warp for single-GPU steps, two for peer-exchange steps (fused_impl.cuh)
+    names = {"6": "3 E-warps per S-warp (16 warps, 128 registers)", "5": "2 E-warps per S-warp (12 warps, 168 registers)"}
     vsel = os.environ.get("VS_FUSED_VARIANT", "")
-    variant = {"": "3 E-warps per S-warp (16 warps, 128 registers)", "0": "3 E-warps per S-warp (16 warps, 128 registers)",
-               "6": "3 E-warps per S-warp (16 warps, 128 registers)", "5": "2 E-warps per S-warp (12 warps, 168 registers)"}.get(vsel, "variant %s" % vsel)
+    variant = names.get(vsel if vsel in names else ("6" if world == 1 else "5"), "variant %s" % vsel)
     line = {
         "metric": METRIC, "value": evals(n) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

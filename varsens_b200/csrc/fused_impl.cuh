@@ -1340,15 +1340,19 @@ __global__ void shift_kernel(SourceDev src, FusedConst<K> fc, F f, double *out) 
 //   5 = E/S warp-specialised, 2 E-warps per S-warp, DMMA Gram   6 = same with 3 E-warps per S-warp     (one launch per step)
 // default: 6 (k <= 18: 1-13 % faster than 5, tools/variant_sweep.py).  At k >= 20 the 12-warp form (168 registers per thread, no
 // spills) was the faster one while generation was table-bound (n = 2^24: 4.79 vs 5.06 ms); since the PTX digit step and the
-// computed terms it is the other way round for the generic functor -- k = 20: 4.45 vs 4.51 ms per step at n = 2^24, 0.587 vs
-// 0.598 ms at n = 2^21 (the per-rank rows of an 8-GPU run), same-box A/B -- and only the separable shortcut still prefers 5
-// (3.02 vs 3.21 ms).
+// computed terms it is the other way round for the generic functor on ONE GPU -- k = 20, n = 2^24: 4.45 vs 4.51 ms per step,
+// same-box A/B.  It is also the less even one: its slowest CTA finishes 15-60 us after the others (12 E-warps share the batches
+// of a CTA less evenly than 8) and its kernel time jitters by 0.5 % against 0.02 %, which the peer-memory step of a multi-GPU
+// run pays as waiting for the slowest rank: 8 GPUs 0.647 vs 0.635 ms per step, e2e 0.737 vs 0.707.  So: 6 for single-GPU steps
+// of at least 2^22 rows with the generic functor; 5 for peer-exchange steps, small shards and the separable shortcut (3.02 vs
+// 3.21 ms).
 template <int K>
-static int fused_variant_for(const vs_ctx *c, bool second, bool separable = false) {
+static int fused_variant_for(const vs_ctx *c, bool second, bool separable, uint64_t rows, bool peer) {
     if (!second) return 1;
     const int v = c->opt.fused_variant;
     if (v == 1 || v == 5 || v == 6) return v;
-    return (K >= 20 && separable) ? 5 : 6;
+    if (K < 20) return 6;
+    return (!separable && !peer && rows >= (1ull << 22)) ? 6 : 5;
 }
 
 template <int K, class F, bool SECOND, bool SEPARABLE>
@@ -1364,7 +1368,7 @@ static int launch_fused_t(vs_ctx *c, const SourceDev &src, const FusedConst<K> &
     const uint32_t nterms = src.raw ? 0u : ((foff(K) + 1u) & ~1u);     // even: the table is copied 16 bytes at a time
     const uint64_t rows = i_end - i_begin;
     const uint64_t nbatch = (rows + 31) / 32;
-    const int variant = fused_variant_for<K>(c, SECOND, SEPARABLE);
+    const int variant = fused_variant_for<K>(c, SECOND, SEPARABLE, rows, req && req->mode == 2);
     *finalized = false;
     if constexpr (SECOND) {
         if (variant == 5 || variant == 6) {
@@ -1568,8 +1572,8 @@ static int dispatch_k(vs_ctx *c, const SourceDev &src, const ScaleDev &s, const 
 // The one-launch step (estimators / peer exchange / chunk flags in the kernel's tail) exists for the warp-specialised variants.
 template <int K>
 static bool tail_supported_k(const vs_ctx *c, int flags) {
-    const int v = fused_variant_for<K>(c, (flags & VS_FLAG_SECOND_ORDER) != 0, (flags & VS_FLAG_SEPARABLE) != 0);
-    return v == 5 || v == 6;
+    const int v = fused_variant_for<K>(c, (flags & VS_FLAG_SECOND_ORDER) != 0, (flags & VS_FLAG_SEPARABLE) != 0, 0, false);
+    return v == 5 || v == 6;     // (5 and 6 both have the tail: the choice between them does not matter here)
 }
 
 }  // namespace vs
