@@ -9,11 +9,13 @@ A step = one pass of the whole pipeline over the workload BASELINE.json's metric
 Sobol g-function, k=20, n=2^24 (704,643,072 evaluations), identity scaling, a=[0,.5,3,9,99,99]+[99]*14,
 fused generation + evaluation + reduction, second order included, GENERIC functor path (every point is
 evaluated; the separable prefix/suffix shortcut is reported separately under "separable_shortcut").
-N>1 shards the n base rows over ranks (total work fixed -> "strong"); one all-reduce of the partial sums.
+N>1 shards the n base rows over ranks (total work fixed -> "strong"); ONE kernel launch per rank and step: the 907 partial
+sums are exchanged over NVLink peer memory inside the kernel's tail (the NCCL all-reduce arm is timed beside it, "nccl_arm").
 
 `value`   evals/s with the permutation already resident in HBM (device-timed, CUDA events, max over ranks).
 `e2e`     same metric through the public C-ABI call with HOST buffers: the permutation is copied from pinned
-          host memory and the indices are read back to the host inside the timed region, every step.
+          host memory while the one launch polls for it, and the kernel writes the indices to mapped host memory,
+          inside the timed region, every step.
 `roofline` FP64-pipe roofline of the fused kernel: algorithmic flops (6008 per base row at k=20)
           / kernel time (CUDA events around the launch, inside the library) / measured DFMA peak.
 `cpu_baseline` the oracle's vectorised numpy pipeline on all host cores, bounded sample of the same workload.
