@@ -267,6 +267,45 @@ def test_sample_flat_large_property(ctx):
     assert float(out.min()) > 0.0 and float(out.max()) < 1.0
 
 
+def test_c4_full_size_shard_properties(ctx):
+    """BASELINE config 4 at its FULL design size (k = 50, n = 2^22, Halton indices up to 2^23 + 1000): one rank's base-row shard
+    of an 8-GPU export (21.4 GB on the device) -- the column-substitution identities of saltelli.py:119-123 on every block
+    pair checked on the device, a checksum of checksums, bit-equality with a flat-row window of the same rows, and rows
+    from both ends of the shard against the oracle."""
+    import torch
+    k, n = 50, 1 << 22
+    p = perm_of(n)
+    pd = torch.from_numpy(p.astype(numpy.int32)).cuda()
+    i0, i1 = 5 * (n // 8), 6 * (n // 8)
+    rows = i1 - i0
+    out = torch.empty((2 + 2 * k, rows, k), dtype=torch.float64, device="cuda:0")
+    ctx.sample_flat_shard(k, n, pd, i0, i1, out=out)
+    ctx.synchronize()
+    M1, M2 = out[0], out[1]
+    for j in (0, 1, 10, 11, 12, 25, 48, 49):
+        nj, nn = out[2 + j], out[2 + k + j]
+        mask = torch.ones(k, dtype=torch.bool, device="cuda:0")
+        mask[j] = False
+        assert torch.equal(nj[:, mask], M2[:, mask]) and torch.equal(nj[:, j], M1[:, j]), j
+        assert torch.equal(nn[:, mask], M1[:, mask]) and torch.equal(nn[:, j], M2[:, j]), j
+    c1, c2 = M1.sum(0), M2.sum(0)
+    tot = out.sum(dim=(0, 1))
+    assert torch.allclose(tot, (1 + k) * (c1 + c2), rtol=1e-12)
+    assert float(out.min()) > 0.0 and float(out.max()) < 1.0
+    # the same rows through the flat-row window addressing (block N_j[7]) -- two store warps instead of one
+    t = 2 + 7
+    win = torch.empty((rows, k), dtype=torch.float64, device="cuda:0")
+    ctx.sample_flat(k, n, pd, row_begin=t * n + i0, row_end=t * n + i1, out=win)
+    ctx.synchronize()
+    assert torch.equal(win, out[t])
+    del win
+    # oracle rows at both ends of the shard, in M_1, M_2 and two substituted blocks
+    for t in (0, 1, 2 + 13, 2 + k + 49):
+        for r0 in (i0, i1 - 9):
+            want = cport.sample_flat(k, n, row_begin=t * n + r0, row_end=t * n + r0 + 9, perm=p)
+            assert (out[t, r0 - i0:r0 - i0 + 9].cpu().numpy() == want).all(), (t, r0)
+
+
 # ------------------------------------------------------------------------------------------------
 # estimators on given values
 # ------------------------------------------------------------------------------------------------
