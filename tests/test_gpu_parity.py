@@ -619,6 +619,30 @@ def test_c5_rk4_frozen_spec_all_indices(ctx):
     numpy.testing.assert_allclose(got, ref_v, rtol=1e-12, atol=1e-300)
 
 
+def test_c5_rk4_full_size_shards_and_oracle_rows(ctx):
+    """BASELINE config 5 at its FULL size (n = 2^18: 11,010,048 trajectories of 1000 RK4 steps): three ragged shards add up to
+    the single launch within the contract tolerance, and the trajectories of the last 64 base rows of the design agree with
+    the oracle to rounding level."""
+    from varsens_b200 import _cabi
+    k, n = 20, 1 << 18
+    ref = numpy.array([1.0] * 10 + [0.5] * 10)
+    lo, up = ref / 10.0, ref * 10.0
+    sc = _cabi.Scale(_cabi.SCALE_POWER, lo, up)
+    p = perm_of(n)
+    whole = ctx.run_fused(k, n, p, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=sc)
+    acc = None
+    for a, b in ((0, 100001), (100001, 100002), (100002, n)):
+        part = ctx.fused_partials(k, n, p, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=sc, i_begin=a, i_end=b)
+        acc = part if acc is None else acc + part
+    split = ctx.finalize(k, 1, n, acc)
+    for name in NAMES:
+        close(getattr(split, name), getattr(whole, name))
+    assert float(whole.var_y[0]) > 0.0 and numpy.isfinite(whole.sens_2).all()
+    got = ctx.eval_values(k, n, p, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=sc, i_begin=n - 64, i_end=n)
+    want = cport.values(k, n, cport.OBJ_RK4_CHAIN, [0.01, 1000], scale=("power", lo, up), i0=n - 64, i1=n)
+    numpy.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+
+
 # ------------------------------------------------------------------------------------------------
 # host mirror: the reference's API
 # ------------------------------------------------------------------------------------------------
