@@ -457,7 +457,9 @@ class FusedPlan(object):
     structs, peer tables), so that ``run()`` costs one foreign call -- the per-step host overhead matters once the GPU work is
     ~0.6 ms (8-GPU strong scaling of BASELINE config 3).  ``exchange`` = a dist.PeerExchange for the multi-GPU one-launch step
     (rows [i_begin, i_end) are this rank's shard), None for a single GPU.  The buffers passed in must stay alive and unchanged
-    while the plan is used."""
+    while the plan is used.  ``run()`` returns a Result whose arrays are views of one of the plan's TWO output buffers (used
+    alternately): they stay valid until the run after the next one -- copy them to keep them longer.  (Allocating the buffer,
+    the descriptor struct and the eight views per call cost 11 us of Python per step, 1.7 % of an 8-GPU step.)"""
 
     def __init__(self, ctx, k, n, perm, objective, params, discard=0, scale=IDENTITY, raw=None, flags=FLAG_SECOND_ORDER,
                  i_begin=0, i_end=None, exchange=None):
@@ -470,7 +472,18 @@ class FusedPlan(object):
         self._keep = (par, keep, pk, rk, sp)
         self._len = Result.flat_len(self.k, 1) if self.second else 2 + 4 * self.k
         kk = self.k
-        self._offsets = (0, 1, 2, 2 + kk, 2 + 2 * kk, 2 + 3 * kk, 2 + 4 * kk, 2 + 4 * kk + kk * kk)
+        o = (0, 1, 2, 2 + kk, 2 + 2 * kk, 2 + 3 * kk, 2 + 4 * kk, 2 + 4 * kk + kk * kk)
+        self._out = []                                   # two output sets: (flat buffer, vs_result struct, byref, Result views)
+        for _ in range(2):
+            flat = numpy.empty(self._len)
+            base = flat.ctypes.data
+            if self.second:
+                cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5],
+                               base + 8 * o[6], base + 8 * o[7])
+            else:
+                cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5], None, None)
+            self._out.append((flat, cs, ctypes.byref(cs), Result.views(self.k, 1, flat, self.second)))
+        self._turn = 0
         L = lib()
         i_end = n if i_end is None else i_end
         if exchange is None:
@@ -489,21 +502,15 @@ class FusedPlan(object):
                           int(exchange.world), int(exchange.rank), pb, pf)
 
     def run(self):
-        flat = numpy.empty(self._len)
-        base = flat.ctypes.data
-        o = self._offsets
-        if self.second:
-            cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5],
-                           base + 8 * o[6], base + 8 * o[7])
-        else:
-            cs = vs_result(base, base + 8 * o[1], base + 8 * o[2], base + 8 * o[3], base + 8 * o[4], base + 8 * o[5], None, None)
+        self._turn ^= 1
+        _, _, ref, res = self._out[self._turn]
         if self.exchange is None:
-            st = self._fn(*self._args, ctypes.byref(cs))
+            st = self._fn(*self._args, ref)
         else:
-            st = self._fn(*self._args, self.exchange.next_epoch(), ctypes.byref(cs))
+            st = self._fn(*self._args, self.exchange.next_epoch(), ref)
         if st != VS_OK:
             check(st)
-        return Result.views(self.k, 1, flat, self.second)
+        return res
 
 
 Context.fused_plan = lambda self, *a, **kw: FusedPlan(self, *a, **kw)
